@@ -1,0 +1,149 @@
+"""ctypes bindings for the CPU oracle (oracle/liblp_oracle.so) and, when it has been built in the
+authoring container, for the unmodified reference compiled against the serial oneTBB stand-in
+(oracle/_ref/libkaminpar_ref.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs. The product (kaminpar_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref.so")
+ORACLE_LIB = os.path.join(_HERE, "liblp_oracle.so")
+
+U32P = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+I32P = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def _opt(a: Optional[np.ndarray], dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class LPParams(C.Structure):
+    """Mirror of LabelPropagationCoarseningContext / ...RefinementContext
+    (include/kaminpar-shm/kaminpar.h:140-154, :221-228)."""
+
+    _fields_ = [
+        ("num_iterations", C.c_uint32),
+        ("large_degree_threshold", C.c_uint32),
+        ("max_num_neighbors", C.c_uint32),
+        ("impl", C.c_int32),  # 0 SINGLE_PHASE, 1 TWO_PHASE, 2 GROWING_HASH_TABLES
+        ("tie_breaking", C.c_int32),  # 0 GEOMETRIC, 1 UNIFORM
+        ("two_hop_strategy", C.c_int32),  # 0 DISABLE 1 MATCH 2 MATCH_THREADWISE 3 CLUSTER 4 CLUSTER_THREADWISE
+        ("two_hop_threshold", C.c_double),
+        ("isolated_nodes_strategy", C.c_int32),  # 0 KEEP 1 MATCH 2 CLUSTER 3 MATCH_DURING_TWO_HOP 4 CLUSTER_DURING_TWO_HOP
+    ]
+
+
+def default_cluster_params() -> LPParams:
+    # presets.cc:140-153
+    return LPParams(5, 0xFFFFFFFF, 0xFFFFFFFF, 1, 1, 2, 0.5, 3)
+
+
+def default_refine_params() -> LPParams:
+    # presets.cc:339-347
+    return LPParams(5, 0xFFFFFFFF, 0xFFFFFFFF, 0, 1, 0, 0.5, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# Reference (unmodified sources + serial TBB stand-in)
+# ------------------------------------------------------------------------------------------------
+_ref = None
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_LIB)
+        lib.kmpref_version.restype = C.c_char_p
+        lib.kmpref_rearrange_by_degree_buckets.restype = C.c_uint32
+        lib.kmpref_edge_cut.restype = C.c_int64
+        lib.kmpref_max_cluster_weight.restype = C.c_int32
+        _ref = lib
+    return _ref
+
+
+def _garrs(g):
+    return (
+        C.c_uint32(g.n), C.c_uint32(g.m),
+        g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
+        _opt(g.vwgt, np.int32), _opt(g.adjwgt, np.int32),
+    )
+
+
+def ref_rearrange(g, remove_isolated=True):
+    """graph::rearrange_by_degree_buckets (+ remove_isolated_nodes). Returns (graph, old_to_new)."""
+    from kaminpar_b200.graph import CSRGraph
+
+    xadj = np.zeros(g.n + 1, np.uint32)
+    adj = np.zeros(g.m, np.uint32)
+    vw = np.zeros(g.n, np.int32) if g.vwgt is not None else None
+    ew = np.zeros(g.m, np.int32) if g.adjwgt is not None else None
+    o2n = np.zeros(g.n, np.uint32)
+    buckets = np.zeros(34, np.uint32)
+    nb = C.c_uint32(0)
+    n_lp = ref().kmpref_rearrange_by_degree_buckets(
+        *_garrs(g), C.c_int(1 if remove_isolated else 0),
+        xadj.ctypes.data_as(C.c_void_p), adj.ctypes.data_as(C.c_void_p), _opt(vw, np.int32), _opt(ew, np.int32),
+        o2n.ctypes.data_as(C.c_void_p), buckets.ctypes.data_as(C.c_void_p), C.byref(nb),
+    )
+    out = CSRGraph(
+        xadj=xadj[: n_lp + 1].copy(), adjncy=adj, vwgt=None if vw is None else vw[:n_lp].copy(), adjwgt=ew,
+        sorted=True, buckets=buckets,
+    )
+    return out, o2n
+
+
+def ref_lp_cluster(g, seed, max_cluster_weight, desired=0, params=None, num_calls=1):
+    params = params or default_cluster_params()
+    out = np.zeros(g.n * num_calls, np.uint32)
+    ref().kmpref_lp_cluster(
+        *_garrs(g), C.c_int(1 if g.sorted else 0), C.c_int(seed), C.c_int32(max_cluster_weight),
+        C.c_uint32(desired), C.byref(params), C.c_int(num_calls), out.ctypes.data_as(C.c_void_p),
+    )
+    return out if num_calls == 1 else out.reshape(num_calls, g.n)
+
+
+def ref_lp_refine(g, seed, k, max_block_weights, partition, params=None, min_block_weights=None):
+    params = params or default_refine_params()
+    part = np.ascontiguousarray(partition, dtype=np.uint32).copy()
+    bw = np.zeros(k, np.int32)
+    mbw = np.ascontiguousarray(max_block_weights, dtype=np.int32)
+    ref().kmpref_lp_refine(
+        *_garrs(g), C.c_int(1 if g.sorted else 0), C.c_int(seed), C.c_uint32(k), mbw.ctypes.data_as(C.c_void_p),
+        _opt(min_block_weights, np.int32), C.byref(params), part.ctypes.data_as(C.c_void_p),
+        bw.ctypes.data_as(C.c_void_p),
+    )
+    return part, bw
+
+
+def ref_edge_cut(g, k, partition) -> int:
+    part = np.ascontiguousarray(partition, dtype=np.uint32)
+    return int(ref().kmpref_edge_cut(*_garrs(g), C.c_uint32(k), part.ctypes.data_as(C.c_void_p)))
+
+
+def ref_max_cluster_weight(g, k, eps=0.03) -> int:
+    return int(ref().kmpref_max_cluster_weight(
+        C.c_uint32(g.n), C.c_uint32(g.m), g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
+        _opt(g.vwgt, np.int32), C.c_uint32(k), C.c_double(eps)))
+
+
+def ref_max_block_weights(g, k, eps=0.03) -> np.ndarray:
+    out = np.zeros(k, np.int32)
+    ref().kmpref_max_block_weights(
+        C.c_uint32(g.n), C.c_uint32(g.m), g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
+        _opt(g.vwgt, np.int32), C.c_uint32(k), C.c_double(eps), out.ctypes.data_as(C.c_void_p))
+    return out
