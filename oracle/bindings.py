@@ -147,3 +147,168 @@ def ref_max_block_weights(g, k, eps=0.03) -> np.ndarray:
         C.c_uint32(g.n), C.c_uint32(g.m), g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
         _opt(g.vwgt, np.int32), C.c_uint32(k), C.c_double(eps), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Oracle restatement (oracle/lp_oracle.cc)
+# ------------------------------------------------------------------------------------------------
+class OracleParams(C.Structure):
+    _fields_ = LPParams._fields_ + [
+        ("sync_subrounds", C.c_uint32),
+        ("sync_granule_log2", C.c_uint32),
+        ("sync_flags", C.c_uint32),
+    ]
+
+
+class OracleStats(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_uint32),
+        ("moved", C.c_uint32 * 64),
+        ("edges_scanned", C.c_uint64),
+        ("nodes_visited", C.c_uint64),
+        ("num_clusters", C.c_uint32),
+        ("two_hop_ran", C.c_uint32),
+    ]
+
+
+SYNC_SUBROUNDS_DEFAULT = 8
+SYNC_GRANULE_LOG2_DEFAULT = 5
+
+
+def oracle_params(base: LPParams, subrounds=SYNC_SUBROUNDS_DEFAULT, granule_log2=SYNC_GRANULE_LOG2_DEFAULT,
+                  flags=0) -> OracleParams:
+    p = OracleParams()
+    for name, _ in LPParams._fields_:
+        setattr(p, name, getattr(base, name))
+    p.sync_subrounds, p.sync_granule_log2, p.sync_flags = subrounds, granule_log2, flags
+    return p
+
+
+_oracle = None
+
+
+def build_oracle():
+    import subprocess
+
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liblp_oracle.so"])
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_LIB):
+            build_oracle()
+        lib = C.CDLL(ORACLE_LIB)
+        lib.lpo_rearrange_by_degree_buckets.restype = C.c_uint32
+        lib.lpo_edge_cut.restype = C.c_int64
+        lib.lpo_max_cluster_weight.restype = C.c_int32
+        lib.lpo_max_block_weight.restype = C.c_int32
+        lib.lpo_max_cluster_weight.argtypes = [C.c_uint32, C.c_int64, C.c_uint32, C.c_double]
+        lib.lpo_max_block_weight.argtypes = [C.c_int64, C.c_uint32, C.c_double]
+        _oracle = lib
+    return _oracle
+
+
+def graph_buckets(g):
+    """Bucket prefix array (34) + count, as the reference's CSRGraph ctor derives them."""
+    if g.buckets is not None:
+        b = np.ascontiguousarray(g.buckets, dtype=np.uint32)
+        nb = 0
+        for i in range(33, 0, -1):
+            if b[i] != b[i - 1]:
+                nb = i
+                break
+        return b, nb
+    b = np.zeros(34, np.uint32)
+    nb = C.c_uint32(0)
+    oracle().lpo_degree_buckets(C.c_uint32(g.n), g.xadj.ctypes.data_as(C.c_void_p), C.c_int(1 if g.sorted else 0),
+                                b.ctypes.data_as(C.c_void_p), C.byref(nb))
+    return b, nb.value
+
+
+def oracle_rearrange(g, remove_isolated=True):
+    from kaminpar_b200.graph import CSRGraph
+
+    xadj = np.zeros(g.n + 1, np.uint32)
+    adj = np.zeros(g.m, np.uint32)
+    vw = np.zeros(g.n, np.int32) if g.vwgt is not None else None
+    ew = np.zeros(g.m, np.int32) if g.adjwgt is not None else None
+    o2n = np.zeros(g.n, np.uint32)
+    buckets = np.zeros(34, np.uint32)
+    nb = C.c_uint32(0)
+    n_lp = oracle().lpo_rearrange_by_degree_buckets(
+        *_garrs(g), C.c_int(1 if remove_isolated else 0),
+        xadj.ctypes.data_as(C.c_void_p), adj.ctypes.data_as(C.c_void_p), _opt(vw, np.int32), _opt(ew, np.int32),
+        o2n.ctypes.data_as(C.c_void_p), buckets.ctypes.data_as(C.c_void_p), C.byref(nb),
+    )
+    out = CSRGraph(
+        xadj=xadj[: n_lp + 1].copy(), adjncy=adj, vwgt=None if vw is None else vw[:n_lp].copy(), adjwgt=ew,
+        sorted=True, buckets=buckets,
+    )
+    return out, o2n
+
+
+SEQ, SYNC = 0, 1
+
+
+def oracle_lp_cluster(g, seed, max_cluster_weight, schedule=SEQ, desired=0, params=None, num_calls=1,
+                      communities=None, return_stats=False):
+    if not isinstance(params, OracleParams):
+        params = oracle_params(params or default_cluster_params())
+    b, nb = graph_buckets(g)
+    out = np.zeros(g.n * num_calls, np.uint32)
+    stats = (OracleStats * num_calls)()
+    oracle().lpo_lp_cluster(
+        C.c_int(schedule), *_garrs(g), b.ctypes.data_as(C.c_void_p), C.c_uint32(nb), C.c_int(seed),
+        C.c_int32(max_cluster_weight), C.c_uint32(desired), _opt(communities, np.uint32), C.byref(params),
+        C.c_int(num_calls), out.ctypes.data_as(C.c_void_p), stats,
+    )
+    res = out if num_calls == 1 else out.reshape(num_calls, g.n)
+    return (res, stats) if return_stats else res
+
+
+def oracle_lp_refine(g, seed, k, max_block_weights, partition, schedule=SEQ, params=None, min_block_weights=None,
+                     communities=None, return_stats=False):
+    if not isinstance(params, OracleParams):
+        params = oracle_params(params or default_refine_params())
+    b, nb = graph_buckets(g)
+    part = np.ascontiguousarray(partition, dtype=np.uint32).copy()
+    bw = np.zeros(k, np.int32)
+    mbw = np.ascontiguousarray(max_block_weights, dtype=np.int32)
+    stats = OracleStats()
+    oracle().lpo_lp_refine(
+        C.c_int(schedule), *_garrs(g), b.ctypes.data_as(C.c_void_p), C.c_uint32(nb), C.c_int(seed), C.c_uint32(k),
+        mbw.ctypes.data_as(C.c_void_p), _opt(min_block_weights, np.int32), _opt(communities, np.uint32),
+        C.byref(params), part.ctypes.data_as(C.c_void_p), bw.ctypes.data_as(C.c_void_p), C.byref(stats),
+    )
+    return (part, bw, stats) if return_stats else (part, bw)
+
+
+def oracle_edge_cut(g, partition) -> int:
+    part = np.ascontiguousarray(partition, dtype=np.uint32)
+    return int(oracle().lpo_edge_cut(C.c_uint32(g.n), g.xadj.ctypes.data_as(C.c_void_p),
+                                     g.adjncy.ctypes.data_as(C.c_void_p), _opt(g.adjwgt, np.int32),
+                                     part.ctypes.data_as(C.c_void_p)))
+
+
+def oracle_max_cluster_weight(g, k, eps=0.03) -> int:
+    return int(oracle().lpo_max_cluster_weight(g.n, g.total_node_weight(), k, eps))
+
+
+def oracle_max_block_weights(g, k, eps=0.03) -> np.ndarray:
+    return np.full(k, oracle().lpo_max_block_weight(g.total_node_weight(), k, eps), np.int32)
+
+
+def oracle_sync_select_all(mode, g, labels, weights, max_weights=None, max_cluster_weight=0, min_weights=None,
+                           seed=0, call=0, iteration=0):
+    labels = np.ascontiguousarray(labels, np.uint32)
+    weights = np.ascontiguousarray(weights, np.int32)
+    tgt = np.zeros(g.n, np.uint32)
+    fav = np.zeros(g.n, np.uint32)
+    oracle().lpo_sync_select_all(
+        C.c_int(mode), C.c_uint32(g.n), g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
+        _opt(g.vwgt, np.int32), _opt(g.adjwgt, np.int32), labels.ctypes.data_as(C.c_void_p),
+        weights.ctypes.data_as(C.c_void_p), C.c_uint32(len(weights)), _opt(max_weights, np.int32),
+        C.c_int32(max_cluster_weight), _opt(min_weights, np.int32), C.c_int(seed), C.c_uint32(call),
+        C.c_uint32(iteration), tgt.ctypes.data_as(C.c_void_p), fav.ctypes.data_as(C.c_void_p))
+    return tgt, fav
