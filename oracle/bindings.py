@@ -156,7 +156,7 @@ class OracleParams(C.Structure):
     _fields_ = LPParams._fields_ + [
         ("sync_subrounds", C.c_uint32),
         ("sync_granule_log2", C.c_uint32),
-        ("sync_flags", C.c_uint32),
+        ("sync_commit_passes", C.c_uint32),
     ]
 
 
@@ -172,15 +172,15 @@ class OracleStats(C.Structure):
 
 
 SYNC_SUBROUNDS_DEFAULT = 8
-SYNC_GRANULE_LOG2_DEFAULT = 5
+SYNC_GRANULE_LOG2_DEFAULT = 4
 
 
 def oracle_params(base: LPParams, subrounds=SYNC_SUBROUNDS_DEFAULT, granule_log2=SYNC_GRANULE_LOG2_DEFAULT,
-                  flags=0) -> OracleParams:
+                  commit_passes=1) -> OracleParams:
     p = OracleParams()
     for name, _ in LPParams._fields_:
         setattr(p, name, getattr(base, name))
-    p.sync_subrounds, p.sync_granule_log2, p.sync_flags = subrounds, granule_log2, flags
+    p.sync_subrounds, p.sync_granule_log2, p.sync_commit_passes = subrounds, granule_log2, commit_passes
     return p
 
 

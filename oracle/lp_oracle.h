@@ -37,7 +37,7 @@ typedef struct {
   /* sync schedule only */
   uint32_t sync_subrounds;    /* S >= 1 */
   uint32_t sync_granule_log2; /* vertices u>>g share a sub-round */
-  uint32_t sync_flags;        /* bit0: direction filter */
+  uint32_t sync_commit_passes; /* commit passes crediting departures (>=1) */
 } lpo_params;
 
 typedef struct {
