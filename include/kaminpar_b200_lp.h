@@ -1,0 +1,154 @@
+/* kaminpar_b200 -- C ABI of the B200-native label-propagation engine.
+ *
+ * This is the drop-in boundary. The reference has no FFI below its C++ plugin
+ * interfaces; the entry points here are what a binding for those interfaces would call:
+ *
+ *   kmp_lp_cluster  <->  Clusterer::compute_clustering(StaticArray<NodeID>&, const Graph&, bool)
+ *                        kaminpar-shm/coarsening/clusterer.h:35-46, implemented by LPClustering
+ *                        (kaminpar-shm/coarsening/clustering/lp_clusterer.cc:376-399)
+ *   kmp_lp_refine   <->  Refiner::initialize(const PartitionedGraph&) + Refiner::refine(
+ *                        PartitionedGraph&, const PartitionContext&)
+ *                        kaminpar-shm/refinement/refiner.h:34-56, implemented by
+ *                        LabelPropagationRefiner (kaminpar-shm/refinement/lp/lp_refiner.cc:357-376)
+ *   kmp_lp_config   <->  LabelPropagationCoarseningContext / LabelPropagationRefinementContext
+ *                        include/kaminpar-shm/kaminpar.h:140-154, :221-228 (same field names)
+ *   kmp_lp_set_graph<->  the CSRGraph the reference hands to both (xadj/adjncy/vwgt/adjwgt,
+ *                        kaminpar-shm/datastructures/csr_graph.h:35-482); empty weight arrays mean
+ *                        unit weights (csr_graph.cc:82-97) -> NULL here
+ *
+ * Type widths are the reference's default build (kaminpar.h:32-57): NodeID = EdgeID = BlockID =
+ * uint32_t, NodeWeight = EdgeWeight = BlockWeight = int32_t. All arithmetic on the path is integer.
+ *
+ * Error convention: every call returns 0 on success or a negative kmp_status; kmp_last_error()
+ * returns a description for the calling thread. There is no CPU fallback: without a CUDA device
+ * every compute entry point fails with KMP_ERR_CUDA.
+ */
+#ifndef KAMINPAR_B200_LP_H
+#define KAMINPAR_B200_LP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMP_LP_ABI_VERSION 1
+
+typedef enum {
+  KMP_OK = 0,
+  KMP_ERR_INVALID = -1,     /* bad argument / call order */
+  KMP_ERR_CUDA = -2,        /* CUDA runtime failure (incl. no device) */
+  KMP_ERR_ALLOC = -3,       /* device or host allocation failed */
+  KMP_ERR_UNSUPPORTED = -4, /* e.g. compressed graphs, 64-bit ids */
+  KMP_ERR_NCCL = -5
+} kmp_status;
+
+/* enums mirror include/kaminpar-shm/kaminpar.h:100-126 */
+enum { KMP_LP_SINGLE_PHASE = 0, KMP_LP_TWO_PHASE = 1, KMP_LP_GROWING_HASH_TABLES = 2 };
+enum { KMP_TIE_GEOMETRIC = 0, KMP_TIE_UNIFORM = 1 };
+enum { KMP_TWO_HOP_DISABLE = 0, KMP_TWO_HOP_MATCH = 1, KMP_TWO_HOP_MATCH_THREADWISE = 2,
+       KMP_TWO_HOP_CLUSTER = 3, KMP_TWO_HOP_CLUSTER_THREADWISE = 4 };
+enum { KMP_ISOLATED_KEEP = 0, KMP_ISOLATED_MATCH = 1, KMP_ISOLATED_CLUSTER = 2,
+       KMP_ISOLATED_MATCH_DURING_TWO_HOP = 3, KMP_ISOLATED_CLUSTER_DURING_TWO_HOP = 4 };
+
+typedef struct {
+  /* fields of LabelPropagation{Coarsening,Refinement}Context, same names and defaults
+   * (kaminpar-shm/presets.cc:140-153, :339-347) */
+  uint32_t num_iterations;         /* 5; refiner: 0 = until no vertex moves */
+  uint32_t large_degree_threshold; /* UINT32_MAX: vertices with degree >= this are never moved */
+  uint32_t max_num_neighbors;      /* UINT32_MAX: scan at most this many neighbours per vertex */
+  int32_t impl;                    /* accepted for API compatibility; every implementation choice of
+                                      the reference has the same observable selection rule */
+  int32_t tie_breaking_strategy;   /* KMP_TIE_UNIFORM (GEOMETRIC is mapped to UNIFORM: both pick
+                                      uniformly among maximal candidates) */
+  int32_t two_hop_strategy;        /* clusterer only */
+  double two_hop_threshold;        /* 0.5 */
+  int32_t isolated_nodes_strategy; /* clusterer only */
+  int32_t relabel_before_second_phase; /* accepted, no effect (no second phase on the GPU) */
+  /* engine */
+  int32_t seed;                /* Random::reseed() analogue; enters every hash key */
+  uint32_t sync_subrounds;     /* S: hashed sub-rounds per degree group and iteration (8) */
+  uint32_t sync_granule_log2;  /* vertices u >> g share a sub-round (4) */
+  uint32_t sync_commit_passes; /* commit passes crediting departures: 1 clusterer, 4 refiner */
+  int32_t device;              /* CUDA device ordinal, -1 = current */
+} kmp_lp_config;
+
+typedef struct {
+  uint32_t iterations;       /* LP rounds executed */
+  uint32_t moved[64];        /* accepted moves per round */
+  uint64_t edges_scanned;    /* sum of scanned adjacency entries of visited active vertices */
+  uint64_t nodes_visited;
+  uint64_t proposals;        /* vertices that wanted to move */
+  uint32_t num_clusters;     /* clusterer: non-empty clusters after the rounds (before post passes) */
+  uint32_t two_hop_ran;
+  float device_ms;           /* CUDA-event time of the whole call on the handle's stream */
+  float sweep_ms;            /* CUDA-event time spent in the sweep kernels only (if timing enabled) */
+  uint64_t sweep_launches;   /* number of sweep-kernel launches */
+  uint64_t kernel_launches;  /* all kernel launches of the call */
+} kmp_lp_stats;
+
+typedef struct kmp_lp_handle kmp_lp_handle;
+
+int kmp_lp_abi_version(void);
+const char *kmp_last_error(void);
+
+/* Fill cfg with the default-preset values for the clusterer (mode 0) or refiner (mode 1). */
+void kmp_lp_default_config(int mode, kmp_lp_config *cfg);
+
+int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out);
+int kmp_lp_destroy(kmp_lp_handle *h);
+
+/* Borrow a CSR graph from HOST memory: copies it to the device (pinned staging when the buffers
+ * are pageable). vwgt / adjwgt may be NULL (unit weights). The handle keeps device copies until the
+ * next set_graph / destroy. */
+int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *xadj,
+                     const uint32_t *adjncy, const int32_t *vwgt, const int32_t *adjwgt);
+/* Same, but the arrays already live in device memory of the handle's device and stay owned by the
+ * caller (must outlive their use by the handle). */
+int kmp_lp_set_graph_device(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *d_xadj,
+                            const uint32_t *d_adjncy, const int32_t *d_vwgt, const int32_t *d_adjwgt);
+
+/* LPClustering::set_max_cluster_weight / set_desired_cluster_count / set_communities +
+ * compute_clustering. clustering_out: HOST buffer of n NodeIDs (cluster = id of a vertex in
+ * [0,n), not compacted) or NULL to leave the result on the device (kmp_lp_labels_device).
+ * communities: HOST, nullable. Every call advances the handle's call counter (overlay coarsener:
+ * same graph, different clustering, overlay_cluster_coarsener.cc:52-54). */
+int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desired_num_clusters,
+                   const uint32_t *communities, uint32_t *clustering_out, kmp_lp_stats *stats);
+
+/* LabelPropagationRefiner::refine. partition_inout: HOST buffer of n BlockIDs, refined in place
+ * (NULL: operate on the partition already on the device from kmp_lp_upload_partition).
+ * max_block_weights[k] (PartitionContext::max_block_weight, per block), min_block_weights[k]
+ * nullable (PartitionContext::min_block_weight). block_weights_out[k] nullable. */
+int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights,
+                  const int32_t *min_block_weights, const uint32_t *communities,
+                  uint32_t *partition_inout, int32_t *block_weights_out, kmp_lp_stats *stats);
+
+/* Device-resident variants used when the caller keeps state on the GPU between calls. */
+int kmp_lp_upload_partition(kmp_lp_handle *h, const uint32_t *partition);
+int kmp_lp_download_labels(kmp_lp_handle *h, uint32_t *labels_out);
+const uint32_t *kmp_lp_labels_device(kmp_lp_handle *h);
+
+/* T0 parity hook: evaluate the per-vertex selection rule for EVERY vertex against frozen labels
+ * and weights (no moves). mode 0: clusterer (weights[n], scalar max), mode 1: refiner (weights[k],
+ * max_weights[k]). Outputs HOST buffers: target[n]; favored[n] (mode 0; UINT32_MAX where the
+ * vertex would not store a favored cluster). */
+int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const int32_t *weights,
+                      uint32_t num_labels, const int32_t *max_weights, int32_t max_cluster_weight,
+                      const int32_t *min_weights, uint32_t call_index, uint32_t iteration,
+                      uint32_t *target_out, uint32_t *favored_out);
+
+/* free_memory_afterwards analogue (lp_clusterer.cc:330-333): release device scratch; the graph
+ * stays. */
+int kmp_lp_free_scratch(kmp_lp_handle *h);
+
+/* Enable per-kernel CUDA-event timing of the sweep kernels (serialises nothing, adds events). */
+int kmp_lp_set_timing(kmp_lp_handle *h, int enabled);
+
+/* Metrics on the device (metrics.cc:36-53): edge cut of the labels currently on the device. */
+int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1137 @@
+// kaminpar_b200: host side of the B200-native label-propagation engine + its C ABI
+// (include/kaminpar_b200_lp.h). One handle = one CUDA stream on one device; everything between
+// the H2D copy of the inputs and the D2H copy of the result runs on the device.
+//
+// Drivers restated (control flow only; the per-vertex work is in lp_sweep.cuh / lp_commit.cuh):
+//   LPClusteringImpl::compute_clustering   kaminpar-shm/coarsening/clustering/lp_clusterer.cc:89-109
+//   LPRefinerImpl::refine                  kaminpar-shm/refinement/lp/lp_refiner.cc:68-89
+//   ChunkRandomLabelPropagation::perform_iteration  kaminpar-shm/label_propagation.h:1681-1733
+// The visit schedule is the "sync" schedule of DESIGN.md instead of the reference's asynchronous
+// chunk-random order (which is only deterministic at one thread).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/kaminpar_b200_lp.h"
+#include "lp_commit.cuh"
+#include "lp_device.cuh"
+#include "lp_sweep.cuh"
+
+using namespace kmp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define KMP_CUDA(expr)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess) {                                                                               \
+      return fail(_e == cudaErrorMemoryAllocation ? KMP_ERR_ALLOC : KMP_ERR_CUDA,                          \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));                                     \
+    }                                                                                                      \
+  } while (0)
+
+constexpr int kNumGroups = 4;
+constexpr int kSMs = 148;
+
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0; // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) {
+      return cudaSuccess;
+    }
+    release();
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+      cap = std::max<size_t>(n, 1);
+    } else {
+      p = nullptr;
+    }
+    return e;
+  }
+  void release() {
+    if (p != nullptr) {
+      cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+} // namespace
+
+struct kmp_lp_handle {
+  kmp_lp_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
+  size_t sweep_events_used = 0;
+
+  // graph
+  uint32_t n = 0, m = 0;
+  const uint32_t *xadj = nullptr;
+  const uint32_t *adjncy = nullptr;
+  const int32_t *vwgt = nullptr;
+  const int32_t *adjwgt = nullptr;
+  DevBuf<uint32_t> own_xadj, own_adjncy;
+  DevBuf<int32_t> own_vwgt, own_adjwgt;
+  bool have_graph = false;
+  uint32_t max_degree = 0;
+  uint32_t num_isolated = 0;
+
+  // work lists: order[] holds the vertices of (group g, sub-round s) contiguously
+  DevBuf<uint32_t> order;
+  std::vector<uint32_t> list_off; // kNumGroups*S + 1 (+1 tail bucket for unvisited vertices)
+  uint32_t max_list = 0;
+  uint32_t lists_S = 0, lists_G = 0, lists_thr = 0;
+  int lists_seed = 0;
+  bool lists_valid = false;
+
+  // state
+  DevBuf<uint32_t> label, favored, communities;
+  DevBuf<int32_t> weight, maxw, minw;
+  DevBuf<uint8_t> active;
+  // scratch
+  DevBuf<uint32_t> mv_u, mv_t, cslot, slotmap;
+  DevBuf<uint8_t> acc;
+  DevBuf<int32_t> incoming, chist, hist, jmin, out_cur, out_delta, ohist, ojmin;
+  DevBuf<uint32_t> ctr32; // [0] mover_count [1] moved_count (per iteration) [2] misc
+  DevBuf<unsigned long long> ctr64; // [0] edges [1] nodes [2] proposals
+  DevBuf<uint32_t> hub_keys;
+  DevBuf<int32_t> hub_vals;
+  uint32_t hub_stride = 0, hub_grid = 0;
+  DevBuf<uint8_t> sort_keys_in, sort_keys_out;
+  DevBuf<uint32_t> sort_vals_in;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<unsigned long long> pairs_a, pairs_b;
+  bool slot_state_clean = false; // incoming/slotmap/chist zeroed for current n
+
+  uint32_t call_counter = 0;
+  uint64_t kernel_launches = 0, sweep_launches = 0;
+};
+
+namespace {
+
+// ---- small kernels --------------------------------------------------------------------------
+__global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32_t granule_log2, uint32_t base_sr,
+                            uint32_t large_degree_threshold, uint8_t *keys, uint32_t *vals, uint32_t *hist,
+                            uint32_t *max_deg) {
+  uint32_t local_max = 0;
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const uint32_t d = xadj[u + 1] - xadj[u];
+    uint32_t key;
+    if (d == 0 || !(d < large_degree_threshold)) {
+      key = kNumGroups * S; // never visited (label_propagation.h:1795, :1914-1915)
+    } else {
+      key = degree_group(d) * S + subround_of(u, granule_log2, base_sr, S);
+    }
+    keys[u] = static_cast<uint8_t>(key);
+    vals[u] = u;
+    atomicAdd(&hist[key], 1u);
+    local_max = d > local_max ? d : local_max;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t other = __shfl_xor_sync(kFull, local_max, o);
+    local_max = other > local_max ? other : local_max;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(max_deg, local_max);
+  }
+}
+
+__global__ void k_init_cluster(uint32_t n, const int32_t *vwgt, uint32_t *label, int32_t *weight, uint32_t *favored,
+                               uint8_t *active) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    label[u] = u; // reset_state, label_propagation.h:1194-1220 with initial_cluster(u) = u
+    favored[u] = u;
+    weight[u] = vwgt != nullptr ? vwgt[u] : 1;
+    active[u] = 1;
+  }
+}
+__global__ void k_fill_u8(uint32_t n, uint8_t *p, uint8_t v) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    p[i] = v;
+  }
+}
+__global__ void k_block_weights(uint32_t n, const int32_t *vwgt, const uint32_t *label, int32_t *weight) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    atomicAdd(&weight[label[u]], vwgt != nullptr ? vwgt[u] : 1);
+  }
+}
+__global__ void k_count_nonzero(uint32_t n, const int32_t *w, uint32_t *out) {
+  uint32_t c = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    c += w[i] != 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(kFull, c, o);
+  }
+  if ((threadIdx.x & 31) == 0 && c != 0) {
+    atomicAdd(out, c);
+  }
+}
+__global__ void k_edge_cut(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *adjwgt,
+                           const uint32_t *label, unsigned long long *out) {
+  unsigned long long c = 0;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t u = warp; u < n; u += nwarps) {
+    const uint32_t lu = label[u];
+    for (uint32_t e = xadj[u] + lane; e < xadj[u + 1]; e += 32) {
+      if (label[adjncy[e]] != lu) {
+        c += adjwgt != nullptr ? adjwgt[e] : 1;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(kFull, c, o);
+  }
+  if (lane == 0 && c != 0) {
+    atomicAdd(out, c);
+  }
+}
+
+// ---- post passes of the clusterer (sync definitions) ---------------------------------
+// isolated nodes: the i-th and (i+1)-th isolated vertex (i even, id order) are matched if they fit
+__global__ void k_collect_isolated(uint32_t n, const uint32_t *xadj, uint32_t *list, uint32_t *count) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    if (xadj[u + 1] == xadj[u]) {
+      list[atomicAdd(count, 1u)] = u;
+    }
+  }
+}
+__global__ void k_match_isolated(uint32_t cnt, const uint32_t *sorted_iso, uint32_t *label, int32_t *weight,
+                                 int32_t max_w) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p + 1 < cnt; p += gridDim.x * blockDim.x) {
+    const uint32_t a = sorted_iso[2 * p], b = sorted_iso[2 * p + 1];
+    const uint32_t ca = label[a], cb = label[b];
+    if (ca != cb && weight[ca] + weight[cb] <= max_w) {
+      weight[ca] += weight[cb];
+      weight[cb] = 0;
+      label[b] = ca;
+    }
+  }
+}
+// two-hop: eligible singletons keyed by (favored, u)
+__global__ void k_collect_two_hop(uint32_t n, const uint32_t *xadj, const int32_t *vwgt, const uint32_t *label,
+                                  const int32_t *weight, const uint32_t *favored, int32_t max_w,
+                                  unsigned long long *pairs, uint32_t *count) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    if (xadj[u + 1] == xadj[u] || label[u] != u) {
+      continue;
+    }
+    const int32_t w = weight[u];
+    const int32_t nw = vwgt != nullptr ? vwgt[u] : 1;
+    if (w > max_w / 2 || w != nw) {
+      continue;
+    }
+    pairs[atomicAdd(count, 1u)] = (static_cast<unsigned long long>(favored[u]) << 32) | u;
+  }
+}
+// head[p] = index of the first element of p's group (equal favored); computed as an inclusive max-scan
+// over (is_head ? p : 0)
+__global__ void k_two_hop_heads(uint32_t cnt, const unsigned long long *sorted, uint32_t *head) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cnt; p += gridDim.x * blockDim.x) {
+    const bool is_head = p == 0 || static_cast<uint32_t>(sorted[p - 1] >> 32) != static_cast<uint32_t>(sorted[p] >> 32);
+    head[p] = is_head ? p : 0u;
+  }
+}
+struct MaxOp {
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+// the (2i+1)-th member of a group joins the (2i)-th (label_propagation.h:977-1002 at one thread)
+__global__ void k_match_two_hop(uint32_t cnt, const unsigned long long *sorted, const uint32_t *head, uint32_t *label,
+                                int32_t *weight) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cnt; p += gridDim.x * blockDim.x) {
+    const uint32_t rank = p - head[p];
+    if (rank & 1u) {
+      const uint32_t rep = static_cast<uint32_t>(sorted[p - 1]);
+      const uint32_t u = static_cast<uint32_t>(sorted[p]);
+      weight[rep] += weight[u];
+      weight[u] = 0;
+      label[u] = rep;
+    }
+  }
+}
+
+// ---- launch helpers -----------------------------------------------------------------------------
+inline uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t max_blocks = kSMs * 16) {
+  const uint64_t b = (threads_needed + block - 1) / block;
+  return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(b, max_blocks)));
+}
+
+template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int group, const SweepArgs &a) {
+  if (a.list_size == 0) {
+    return cudaSuccess;
+  }
+  switch (group) {
+  case 0:
+    sweep_thread<MODE, EW><<<grid_for(a.list_size, 256), 256, 0, h->stream>>>(a);
+    break;
+  case 1:
+    sweep_warp<MODE, EW><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->stream>>>(a);
+    break;
+  case 2:
+    sweep_warp_hash<MODE, EW>
+        <<<grid_for(static_cast<uint64_t>(a.list_size) * 32, kWarpsPerBlockG2 * 32), kWarpsPerBlockG2 * 32, 0,
+           h->stream>>>(a);
+    break;
+  default: {
+    const size_t smem = static_cast<size_t>(kBlockTableSlots) * 8;
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(a.list_size, h->hub_grid));
+    sweep_block<MODE, EW><<<blocks, kBlockThreadsG3, smem, h->stream>>>(a);
+    break;
+  }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs &a) {
+  if (a.list_size == 0) {
+    return cudaSuccess;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (h->timing) {
+    if (h->sweep_events_used == h->sweep_events.size()) {
+      cudaEvent_t x, y;
+      cudaEventCreate(&x);
+      cudaEventCreate(&y);
+      h->sweep_events.emplace_back(x, y);
+    }
+    e0 = h->sweep_events[h->sweep_events_used].first;
+    e1 = h->sweep_events[h->sweep_events_used].second;
+    ++h->sweep_events_used;
+    cudaEventRecord(e0, h->stream);
+  }
+  const bool ew = h->adjwgt != nullptr;
+  cudaError_t e;
+  if (mode == 0) {
+    e = ew ? launch_sweep_t<0, true>(h, group, a) : launch_sweep_t<0, false>(h, group, a);
+  } else {
+    e = ew ? launch_sweep_t<1, true>(h, group, a) : launch_sweep_t<1, false>(h, group, a);
+  }
+  if (h->timing) {
+    cudaEventRecord(e1, h->stream);
+  }
+  ++h->kernel_launches;
+  ++h->sweep_launches;
+  return e;
+}
+
+int ensure_lists(kmp_lp_handle *h) {
+  const uint32_t S = std::max<uint32_t>(1, h->cfg.sync_subrounds);
+  if (h->lists_valid && h->lists_S == S && h->lists_G == h->cfg.sync_granule_log2 &&
+      h->lists_thr == h->cfg.large_degree_threshold && h->lists_seed == h->cfg.seed) {
+    return KMP_OK;
+  }
+  if (kNumGroups * S + 1 > 255) {
+    return fail(KMP_ERR_INVALID, "sync_subrounds too large (max 63)");
+  }
+  const uint32_t n = h->n;
+  const uint32_t nkeys = kNumGroups * S + 1;
+  KMP_CUDA(h->sort_keys_in.ensure(n));
+  KMP_CUDA(h->sort_keys_out.ensure(n));
+  KMP_CUDA(h->sort_vals_in.ensure(n));
+  KMP_CUDA(h->order.ensure(n));
+  KMP_CUDA(h->ctr32.ensure(512));
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
+  const uint32_t base_sr = sync_base(h->cfg.seed, 0, 0, SALT_SUBROUND);
+  k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, h->cfg.sync_granule_log2, base_sr,
+                                                        h->cfg.large_degree_threshold, h->sort_keys_in.p,
+                                                        h->sort_vals_in.p, h->ctr32.p, h->ctr32.p + 300);
+  KMP_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  KMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->sort_keys_in.p, h->sort_keys_out.p,
+                                           h->sort_vals_in.p, h->order.p, static_cast<int>(n), 0, 8, h->stream));
+  KMP_CUDA(h->cub_tmp.ensure(tmp_bytes));
+  if (n > 0) {
+    KMP_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, h->sort_keys_in.p, h->sort_keys_out.p,
+                                             h->sort_vals_in.p, h->order.p, static_cast<int>(n), 0, 8, h->stream));
+  }
+  std::vector<uint32_t> hist(512);
+  KMP_CUDA(cudaMemcpyAsync(hist.data(), h->ctr32.p, 512 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  h->list_off.assign(nkeys + 1, 0);
+  h->max_list = 0;
+  for (uint32_t kx = 0; kx < nkeys; ++kx) {
+    h->list_off[kx + 1] = h->list_off[kx] + hist[kx];
+    if (kx + 1 < nkeys) {
+      h->max_list = std::max(h->max_list, hist[kx]);
+    }
+  }
+  h->max_degree = hist[300];
+  h->lists_S = S;
+  h->lists_G = h->cfg.sync_granule_log2;
+  h->lists_thr = h->cfg.large_degree_threshold;
+  h->lists_seed = h->cfg.seed;
+  h->lists_valid = true;
+  // the sort buffers are only needed here
+  h->sort_keys_in.release();
+  h->sort_keys_out.release();
+  h->sort_vals_in.release();
+  return KMP_OK;
+}
+
+// scratch shared by both modes
+int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
+  const size_t cap = std::max<uint32_t>(h->max_list, 1);
+  KMP_CUDA(h->mv_u.ensure(cap));
+  KMP_CUDA(h->mv_t.ensure(cap));
+  KMP_CUDA(h->acc.ensure(cap));
+  KMP_CUDA(h->ctr32.ensure(512));
+  KMP_CUDA(h->ctr64.ensure(8));
+  KMP_CUDA(h->active.ensure(h->n));
+  if (mode == 0) {
+    KMP_CUDA(h->cslot.ensure(cap));
+    const bool fresh = h->incoming.cap < h->n || h->slotmap.cap < h->n || h->chist.cap < cap * kLadderLevels;
+    KMP_CUDA(h->incoming.ensure(h->n));
+    KMP_CUDA(h->slotmap.ensure(h->n));
+    KMP_CUDA(h->chist.ensure(cap * kLadderLevels));
+    if (fresh || !h->slot_state_clean) {
+      KMP_CUDA(cudaMemsetAsync(h->incoming.p, 0, h->incoming.cap * sizeof(int32_t), h->stream));
+      KMP_CUDA(cudaMemsetAsync(h->slotmap.p, 0xFF, h->slotmap.cap * sizeof(uint32_t), h->stream));
+      KMP_CUDA(cudaMemsetAsync(h->chist.p, 0, h->chist.cap * sizeof(int32_t), h->stream));
+      h->slot_state_clean = true;
+    }
+  } else {
+    const size_t kk = std::max<uint32_t>(num_labels, 1);
+    KMP_CUDA(h->hist.ensure(kk * kLadderLevels));
+    KMP_CUDA(h->ohist.ensure(kk * kLadderLevels));
+    KMP_CUDA(h->jmin.ensure(kk));
+    KMP_CUDA(h->ojmin.ensure(kk));
+    KMP_CUDA(h->out_cur.ensure(kk));
+    KMP_CUDA(h->out_delta.ensure(kk));
+    KMP_CUDA(cudaMemsetAsync(h->hist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
+    KMP_CUDA(cudaMemsetAsync(h->ohist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
+  }
+  // hub tables (global-memory hash maps of sweep_block)
+  const uint32_t distinct = std::min<uint32_t>(h->max_degree, num_labels);
+  h->hub_grid = kSMs * 2;
+  h->hub_stride = 0;
+  if (num_labels > static_cast<uint32_t>(kBlockTableSlots) && 2ull * distinct > static_cast<uint64_t>(kBlockTableSlots)) {
+    uint64_t stride = 1;
+    while (stride < 2ull * distinct) {
+      stride <<= 1;
+    }
+    const uint64_t budget_slots = (2ull << 30) / 8; // 2 GiB of tables
+    uint64_t grid = std::max<uint64_t>(8, std::min<uint64_t>(kSMs * 2, budget_slots / stride));
+    h->hub_grid = static_cast<uint32_t>(grid);
+    h->hub_stride = static_cast<uint32_t>(stride);
+    const size_t slots = static_cast<size_t>(grid) * stride;
+    if (h->hub_keys.cap < slots) {
+      KMP_CUDA(h->hub_keys.ensure(slots));
+      KMP_CUDA(h->hub_vals.ensure(slots));
+      KMP_CUDA(cudaMemsetAsync(h->hub_keys.p, 0xFF, slots * sizeof(uint32_t), h->stream));
+      KMP_CUDA(cudaMemsetAsync(h->hub_vals.p, 0, slots * sizeof(int32_t), h->stream));
+    }
+  }
+  return KMP_OK;
+}
+
+struct RunCtx {
+  int mode;
+  uint32_t num_labels;
+  int32_t max_cluster_weight;
+  bool has_min;
+  bool has_comm;
+};
+
+SweepArgs make_sweep_args(kmp_lp_handle *h, const RunCtx &rc) {
+  SweepArgs a{};
+  a.xadj = h->xadj;
+  a.adjncy = h->adjncy;
+  a.vwgt = h->vwgt;
+  a.adjwgt = h->adjwgt;
+  a.label = h->label.p;
+  a.weight = h->weight.p;
+  a.max_w = rc.mode == 1 ? h->maxw.p : nullptr;
+  a.min_w = rc.has_min ? h->minw.p : nullptr;
+  a.communities = rc.has_comm ? h->communities.p : nullptr;
+  a.active = h->active.p;
+  a.favored = h->favored.p;
+  a.max_cluster_weight = rc.max_cluster_weight;
+  a.num_labels = rc.num_labels;
+  a.max_num_neighbors = h->cfg.max_num_neighbors;
+  a.mv_u = h->mv_u.p;
+  a.mv_t = h->mv_t.p;
+  a.mover_count = h->ctr32.p;
+  a.incoming = h->incoming.p;
+  a.hist = h->hist.p;
+  a.counters = h->ctr64.p;
+  a.sel_target = nullptr;
+  a.sel_favored = nullptr;
+  a.hub_keys = h->hub_keys.p;
+  a.hub_vals = h->hub_vals.p;
+  a.hub_stride = h->hub_stride;
+  return a;
+}
+
+CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
+  CommitArgs c{};
+  c.xadj = h->xadj;
+  c.adjncy = h->adjncy;
+  c.vwgt = h->vwgt;
+  c.label = h->label.p;
+  c.weight = h->weight.p;
+  c.max_w = rc.mode == 1 ? h->maxw.p : nullptr;
+  c.min_w = rc.has_min ? h->minw.p : nullptr;
+  c.active = h->active.p;
+  c.max_cluster_weight = rc.max_cluster_weight;
+  c.k = rc.num_labels;
+  c.mv_u = h->mv_u.p;
+  c.mv_t = h->mv_t.p;
+  c.acc = h->acc.p;
+  c.mover_count = h->ctr32.p;
+  c.incoming = h->incoming.p;
+  c.slotmap = h->slotmap.p;
+  c.cslot = h->cslot.p;
+  c.chist = h->chist.p;
+  c.hist = h->hist.p;
+  c.jmin = h->jmin.p;
+  c.out_cur = h->out_cur.p;
+  c.out_delta = h->out_delta.p;
+  c.ohist = h->ohist.p;
+  c.ojmin = h->ojmin.p;
+  c.moved_count = h->ctr32.p + 1;
+  return c;
+}
+
+// One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
+int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
+  const uint32_t S = h->lists_S;
+  SweepArgs sa = make_sweep_args(h, rc);
+  CommitArgs ca = make_commit_args(h, rc);
+  sa.base_tie = sync_base(h->cfg.seed, h->call_counter, iter, SALT_TIE);
+  sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // mover, moved, proposals
+  const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
+  for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
+    const uint32_t off = h->list_off[sg];
+    const uint32_t size = h->list_off[sg + 1] - off;
+    if (size == 0) {
+      continue;
+    }
+    const int group = static_cast<int>(sg / S);
+    sa.list = h->order.p + off;
+    sa.list_size = size;
+    sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+    ca.base_commit = sa.base_commit;
+    reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
+    KMP_CUDA(launch_sweep(h, rc.mode, group, sa));
+    const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
+    if (rc.mode == 0) {
+      commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
+      commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
+      commit_apply<0><<<cgrid, 256, 0, h->stream>>>(ca);
+      h->kernel_launches += 4;
+    } else {
+      const uint32_t kgrid = grid_for(rc.num_labels, 128);
+      commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p);
+      commit_refine_prepare<<<kgrid, 128, 0, h->stream>>>(ca);
+      for (uint32_t p = 0; p < passes; ++p) {
+        commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
+        commit_refine_decide<<<cgrid, 256, 0, h->stream>>>(ca);
+      }
+      h->kernel_launches += 3 + 2 * passes;
+      if (rc.has_min) {
+        commit_refine_ohist<<<cgrid, 256, 0, h->stream>>>(ca);
+        commit_refine_ojmin<<<kgrid, 128, 0, h->stream>>>(ca);
+        commit_refine_othin<<<cgrid, 256, 0, h->stream>>>(ca);
+        h->kernel_launches += 3;
+      }
+      commit_apply<1><<<cgrid, 256, 0, h->stream>>>(ca);
+      commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
+      h->kernel_launches += 2;
+    }
+    commit_activate<<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca);
+    h->kernel_launches += 1;
+    KMP_CUDA(cudaGetLastError());
+  }
+  uint32_t host[2] = {0, 0};
+  KMP_CUDA(cudaMemcpyAsync(host, h->ctr32.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  *moved = host[1];
+  (void)proposals;
+  return KMP_OK;
+}
+
+int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
+  if (h == nullptr || !h->have_graph) {
+    return fail(KMP_ERR_INVALID, "no graph set");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  if (stats != nullptr) {
+    std::memset(stats, 0, sizeof(*stats));
+  }
+  h->kernel_launches = 0;
+  h->sweep_launches = 0;
+  h->sweep_events_used = 0;
+  KMP_CUDA(cudaEventRecord(h->ev_begin, h->stream));
+  return KMP_OK;
+}
+
+int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
+  KMP_CUDA(cudaEventRecord(h->ev_end, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  if (stats != nullptr) {
+    unsigned long long c[3] = {0, 0, 0};
+    KMP_CUDA(cudaMemcpy(c, h->ctr64.p, sizeof(c), cudaMemcpyDeviceToHost));
+    stats->edges_scanned = c[0];
+    stats->nodes_visited = c[1];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
+    stats->device_ms = ms;
+    float sweep = 0.f;
+    for (size_t i = 0; i < h->sweep_events_used; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, h->sweep_events[i].first, h->sweep_events[i].second);
+      sweep += t;
+    }
+    stats->sweep_ms = sweep;
+    stats->sweep_launches = h->sweep_launches;
+    stats->kernel_launches = h->kernel_launches;
+  }
+  return KMP_OK;
+}
+
+int upload_optional_u32(kmp_lp_handle *h, DevBuf<uint32_t> &buf, const uint32_t *host, size_t n) {
+  if (host == nullptr) {
+    return KMP_OK;
+  }
+  KMP_CUDA(buf.ensure(n));
+  KMP_CUDA(cudaMemcpyAsync(buf.p, host, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  return KMP_OK;
+}
+
+int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, kmp_lp_stats *stats) {
+  const uint32_t n = h->n;
+  const bool two_hop = (1.0 - 1.0 * num_clusters / n) <= h->cfg.two_hop_threshold; // lp_clusterer.cc:164-166
+  const int iso = h->cfg.isolated_nodes_strategy;
+  const bool do_iso = (iso == KMP_ISOLATED_MATCH || iso == KMP_ISOLATED_CLUSTER ||
+                       ((iso == KMP_ISOLATED_MATCH_DURING_TWO_HOP || iso == KMP_ISOLATED_CLUSTER_DURING_TWO_HOP) && two_hop));
+  if (do_iso && h->num_isolated > 1) {
+    KMP_CUDA(h->pairs_a.ensure(h->num_isolated)); // reuse as u32 storage
+    KMP_CUDA(h->pairs_b.ensure(h->num_isolated));
+    uint32_t *iso_in = reinterpret_cast<uint32_t *>(h->pairs_a.p);
+    uint32_t *iso_out = reinterpret_cast<uint32_t *>(h->pairs_b.p);
+    reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
+    k_collect_isolated<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, iso_in, h->ctr32.p + 2);
+    uint32_t iso_cnt = 0;
+    KMP_CUDA(cudaMemcpyAsync(&iso_cnt, h->ctr32.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    KMP_CUDA(cudaStreamSynchronize(h->stream));
+    if (iso_cnt > 1) {
+      size_t tmp = 0;
+      KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, iso_in, iso_out, static_cast<int>(iso_cnt), 0, 32, h->stream));
+      KMP_CUDA(h->cub_tmp.ensure(tmp));
+      KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp, iso_in, iso_out, static_cast<int>(iso_cnt), 0, 32, h->stream));
+      k_match_isolated<<<grid_for(iso_cnt / 2 + 1, 256), 256, 0, h->stream>>>(iso_cnt, iso_out, h->label.p, h->weight.p, max_w);
+      h->kernel_launches += 3;
+      KMP_CUDA(cudaGetLastError());
+    }
+  }
+  if (!two_hop || h->cfg.two_hop_strategy == KMP_TWO_HOP_DISABLE) {
+    return KMP_OK;
+  }
+  if (stats != nullptr) {
+    stats->two_hop_ran = 1;
+  }
+  KMP_CUDA(h->pairs_a.ensure(n));
+  KMP_CUDA(h->pairs_b.ensure(n));
+  reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
+  k_collect_two_hop<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, h->vwgt, h->label.p, h->weight.p,
+                                                              h->favored.p, max_w, h->pairs_a.p, h->ctr32.p + 2);
+  uint32_t cnt = 0;
+  KMP_CUDA(cudaMemcpyAsync(&cnt, h->ctr32.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  if (cnt > 1) {
+    size_t tmp = 0;
+    KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0, 64,
+                                            h->stream));
+    KMP_CUDA(h->cub_tmp.ensure(tmp));
+    KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0,
+                                            64, h->stream));
+    // group heads: reuse mv-independent scratch (pairs_a is free after the sort)
+    uint32_t *head_in = reinterpret_cast<uint32_t *>(h->pairs_a.p);
+    uint32_t *head_out = head_in + cnt;
+    k_two_hop_heads<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_in);
+    size_t tmp2 = 0;
+    KMP_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
+    KMP_CUDA(h->cub_tmp.ensure(tmp2));
+    KMP_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
+    k_match_two_hop<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_out, h->label.p, h->weight.p);
+    h->kernel_launches += 5;
+    KMP_CUDA(cudaGetLastError());
+  }
+  return KMP_OK;
+}
+
+} // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int kmp_lp_abi_version(void) { return KMP_LP_ABI_VERSION; }
+
+const char *kmp_last_error(void) { return g_last_error.c_str(); }
+
+void kmp_lp_default_config(int mode, kmp_lp_config *cfg) {
+  if (cfg == nullptr) {
+    return;
+  }
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->num_iterations = 5;                   // presets.cc:143 / :342
+  cfg->large_degree_threshold = 0xFFFFFFFFu; // :144 / :343
+  cfg->max_num_neighbors = 0xFFFFFFFFu;      // :145 / :344
+  cfg->tie_breaking_strategy = KMP_TIE_UNIFORM;
+  cfg->two_hop_threshold = 0.5;
+  cfg->seed = 0;
+  cfg->sync_subrounds = 8;
+  cfg->sync_granule_log2 = 4;
+  cfg->device = -1;
+  if (mode == 0) {
+    cfg->impl = KMP_LP_TWO_PHASE;                                     // :146
+    cfg->two_hop_strategy = KMP_TWO_HOP_MATCH_THREADWISE;             // :148
+    cfg->isolated_nodes_strategy = KMP_ISOLATED_MATCH_DURING_TWO_HOP; // :150-151
+    cfg->sync_commit_passes = 1;
+  } else {
+    cfg->impl = KMP_LP_SINGLE_PHASE; // :345
+    cfg->two_hop_strategy = KMP_TWO_HOP_DISABLE;
+    cfg->isolated_nodes_strategy = KMP_ISOLATED_KEEP;
+    cfg->sync_commit_passes = 4;
+  }
+}
+
+int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
+  if (cfg == nullptr || out == nullptr) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return fail(KMP_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                  cudaGetErrorString(e));
+  }
+  kmp_lp_handle *h = new (std::nothrow) kmp_lp_handle();
+  if (h == nullptr) {
+    return fail(KMP_ERR_ALLOC, "out of host memory");
+  }
+  h->cfg = *cfg;
+  if (h->cfg.sync_subrounds == 0) {
+    h->cfg.sync_subrounds = 8;
+  }
+  if (h->cfg.sync_commit_passes == 0) {
+    h->cfg.sync_commit_passes = 1;
+  }
+  int dev = cfg->device;
+  if (dev < 0) {
+    cudaGetDevice(&dev);
+  }
+  h->device = dev;
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev_begin) != cudaSuccess || cudaEventCreate(&h->ev_end) != cudaSuccess) {
+    delete h;
+    return fail(KMP_ERR_CUDA, "failed to create stream/events");
+  }
+  {
+    const int smem = kBlockTableSlots * 8;
+    cudaFuncSetAttribute(sweep_block<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sweep_block<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sweep_block<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(sweep_block<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  }
+  *out = h;
+  return KMP_OK;
+}
+
+int kmp_lp_destroy(kmp_lp_handle *h) {
+  if (h == nullptr) {
+    return KMP_OK;
+  }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  kmp_lp_free_scratch(h);
+  h->own_xadj.release();
+  h->own_adjncy.release();
+  h->own_vwgt.release();
+  h->own_adjwgt.release();
+  h->order.release();
+  for (auto &p : h->sweep_events) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  cudaEventDestroy(h->ev_begin);
+  cudaEventDestroy(h->ev_end);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return KMP_OK;
+}
+
+int kmp_lp_set_timing(kmp_lp_handle *h, int enabled) {
+  if (h == nullptr) {
+    return fail(KMP_ERR_INVALID, "null handle");
+  }
+  h->timing = enabled != 0;
+  return KMP_OK;
+}
+
+static int set_graph_common(kmp_lp_handle *h, uint32_t n, uint32_t m) {
+  h->n = n;
+  h->m = m;
+  h->have_graph = true;
+  h->lists_valid = false;
+  h->slot_state_clean = false;
+  int rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  h->num_isolated = 0;
+  {
+    // vertices in the tail bucket are either isolated or above the degree threshold; count isolated
+    // ones exactly only when a post pass needs them (cheap: tail bucket size is an upper bound)
+    const uint32_t S = h->lists_S;
+    h->num_isolated = h->list_off[kNumGroups * S + 1] - h->list_off[kNumGroups * S];
+  }
+  return KMP_OK;
+}
+
+int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *xadj, const uint32_t *adjncy,
+                     const int32_t *vwgt, const int32_t *adjwgt) {
+  if (h == nullptr || xadj == nullptr || (m > 0 && adjncy == nullptr)) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  KMP_CUDA(h->own_xadj.ensure(static_cast<size_t>(n) + 1));
+  KMP_CUDA(h->own_adjncy.ensure(m));
+  KMP_CUDA(cudaMemcpyAsync(h->own_xadj.p, xadj, (static_cast<size_t>(n) + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (m > 0) {
+    KMP_CUDA(cudaMemcpyAsync(h->own_adjncy.p, adjncy, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->xadj = h->own_xadj.p;
+  h->adjncy = h->own_adjncy.p;
+  h->vwgt = nullptr;
+  h->adjwgt = nullptr;
+  if (vwgt != nullptr) {
+    KMP_CUDA(h->own_vwgt.ensure(n));
+    KMP_CUDA(cudaMemcpyAsync(h->own_vwgt.p, vwgt, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+    h->vwgt = h->own_vwgt.p;
+  }
+  if (adjwgt != nullptr) {
+    KMP_CUDA(h->own_adjwgt.ensure(m));
+    KMP_CUDA(cudaMemcpyAsync(h->own_adjwgt.p, adjwgt, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h->stream));
+    h->adjwgt = h->own_adjwgt.p;
+  }
+  return set_graph_common(h, n, m);
+}
+
+int kmp_lp_set_graph_device(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *d_xadj, const uint32_t *d_adjncy,
+                            const int32_t *d_vwgt, const int32_t *d_adjwgt) {
+  if (h == nullptr || d_xadj == nullptr || (m > 0 && d_adjncy == nullptr)) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  h->xadj = d_xadj;
+  h->adjncy = d_adjncy;
+  h->vwgt = d_vwgt;
+  h->adjwgt = d_adjwgt;
+  return set_graph_common(h, n, m);
+}
+
+int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desired_num_clusters,
+                   const uint32_t *communities, uint32_t *clustering_out, kmp_lp_stats *stats) {
+  int rc = begin_call(h, stats);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  const uint32_t n = h->n;
+  rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(h->label.ensure(n));
+  KMP_CUDA(h->favored.ensure(n));
+  KMP_CUDA(h->weight.ensure(n));
+  rc = ensure_scratch(h, 0, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  rc = upload_optional_u32(h, h->communities, communities, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  if (n > 0) {
+    k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p,
+                                                            h->active.p);
+    ++h->kernel_launches;
+  }
+  RunCtx ctx{0, n, max_cluster_weight, false, communities != nullptr};
+  uint32_t num_clusters = n;
+  for (uint32_t it = 0; it < h->cfg.num_iterations && n > 0; ++it) { // lp_clusterer.cc:94-105
+    uint32_t moved = 0;
+    rc = run_iteration(h, ctx, it, &moved, nullptr);
+    if (rc != KMP_OK) {
+      return rc;
+    }
+    if (stats != nullptr && it < 64) {
+      stats->moved[it] = moved;
+      stats->iterations = it + 1;
+    }
+    if (moved == 0) {
+      break;
+    }
+    if (desired_num_clusters > 0) { // should_stop(), label_propagation.h:260-265
+      reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
+      k_count_nonzero<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->weight.p, h->ctr32.p + 2);
+      KMP_CUDA(cudaMemcpyAsync(&num_clusters, h->ctr32.p + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+      KMP_CUDA(cudaStreamSynchronize(h->stream));
+      if (num_clusters <= desired_num_clusters) {
+        break;
+      }
+    }
+  }
+  if (n > 0) {
+    reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
+    k_count_nonzero<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->weight.p, h->ctr32.p + 2);
+    KMP_CUDA(cudaMemcpyAsync(&num_clusters, h->ctr32.p + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    KMP_CUDA(cudaStreamSynchronize(h->stream));
+    h->kernel_launches += 2;
+    if (stats != nullptr) {
+      stats->num_clusters = num_clusters;
+    }
+    rc = cluster_post_passes(h, max_cluster_weight, num_clusters, stats); // lp_clusterer.cc:107-108
+    if (rc != KMP_OK) {
+      return rc;
+    }
+  }
+  if (clustering_out != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(clustering_out, h->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  ++h->call_counter;
+  return end_call(h, stats);
+}
+
+int kmp_lp_upload_partition(kmp_lp_handle *h, const uint32_t *partition) {
+  if (h == nullptr || !h->have_graph || partition == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  KMP_CUDA(h->label.ensure(h->n));
+  KMP_CUDA(cudaMemcpyAsync(h->label.p, partition, static_cast<size_t>(h->n) * 4, cudaMemcpyHostToDevice, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  return KMP_OK;
+}
+
+int kmp_lp_download_labels(kmp_lp_handle *h, uint32_t *labels_out) {
+  if (h == nullptr || !h->have_graph || labels_out == nullptr || h->label.p == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  KMP_CUDA(cudaMemcpyAsync(labels_out, h->label.p, static_cast<size_t>(h->n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  return KMP_OK;
+}
+
+const uint32_t *kmp_lp_labels_device(kmp_lp_handle *h) { return h != nullptr ? h->label.p : nullptr; }
+
+int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights, const int32_t *min_block_weights,
+                  const uint32_t *communities, uint32_t *partition_inout, int32_t *block_weights_out,
+                  kmp_lp_stats *stats) {
+  if (max_block_weights == nullptr || k == 0) {
+    return fail(KMP_ERR_INVALID, "max_block_weights / k missing");
+  }
+  int rc = begin_call(h, stats);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  const uint32_t n = h->n;
+  rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(h->label.ensure(n));
+  KMP_CUDA(h->weight.ensure(k));
+  KMP_CUDA(h->maxw.ensure(k));
+  rc = ensure_scratch(h, 1, k);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  if (partition_inout != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(h->label.p, partition_inout, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  KMP_CUDA(cudaMemcpyAsync(h->maxw.p, max_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (min_block_weights != nullptr) {
+    KMP_CUDA(h->minw.ensure(k));
+    KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = upload_optional_u32(h, h->communities, communities, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
+  if (n > 0) {
+    k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
+    k_fill_u8<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->active.p, 1); // Base::initialize: all active
+    h->kernel_launches += 2;
+  }
+  RunCtx ctx{1, k, 0, min_block_weights != nullptr, communities != nullptr};
+  const uint64_t max_it = h->cfg.num_iterations == 0 ? ~0ull : h->cfg.num_iterations; // lp_refiner.cc:78-79
+  for (uint64_t it = 0; it < max_it && n > 0; ++it) {
+    uint32_t moved = 0;
+    rc = run_iteration(h, ctx, static_cast<uint32_t>(it), &moved, nullptr);
+    if (rc != KMP_OK) {
+      return rc;
+    }
+    if (stats != nullptr && it < 64) {
+      stats->moved[it] = moved;
+      stats->iterations = static_cast<uint32_t>(it + 1);
+    }
+    if (moved == 0) {
+      break;
+    }
+  }
+  if (partition_inout != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(partition_inout, h->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (block_weights_out != nullptr) {
+    KMP_CUDA(cudaMemcpyAsync(block_weights_out, h->weight.p, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  return end_call(h, stats);
+}
+
+int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const int32_t *weights, uint32_t num_labels,
+                      const int32_t *max_weights, int32_t max_cluster_weight, const int32_t *min_weights,
+                      uint32_t call_index, uint32_t iteration, uint32_t *target_out, uint32_t *favored_out) {
+  int rc = begin_call(h, nullptr);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  if (labels == nullptr || weights == nullptr || target_out == nullptr || (mode == 1 && max_weights == nullptr)) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  const uint32_t n = h->n;
+  rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(h->label.ensure(n));
+  KMP_CUDA(h->weight.ensure(num_labels));
+  rc = ensure_scratch(h, mode, num_labels);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  DevBuf<uint32_t> d_target, d_fav;
+  KMP_CUDA(d_target.ensure(n));
+  KMP_CUDA(d_fav.ensure(n));
+  KMP_CUDA(cudaMemcpyAsync(h->label.p, labels, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(d_target.p, labels, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  KMP_CUDA(cudaMemsetAsync(d_fav.p, 0xFF, static_cast<size_t>(n) * 4, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(h->weight.p, weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (mode == 1) {
+    KMP_CUDA(h->maxw.ensure(num_labels));
+    KMP_CUDA(cudaMemcpyAsync(h->maxw.p, max_weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (min_weights != nullptr) {
+      KMP_CUDA(h->minw.ensure(num_labels));
+      KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
+  SweepArgs sa = make_sweep_args(h, ctx);
+  sa.active = nullptr;
+  sa.sel_target = d_target.p;
+  sa.sel_favored = mode == 0 ? d_fav.p : nullptr;
+  sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
+  sa.base_fav = sync_base(h->cfg.seed, call_index, iteration, SALT_FAV);
+  const uint32_t S = h->lists_S;
+  for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
+    const uint32_t off = h->list_off[sg];
+    const uint32_t size = h->list_off[sg + 1] - off;
+    sa.list = h->order.p + off;
+    sa.list_size = size;
+    KMP_CUDA(launch_sweep(h, mode, static_cast<int>(sg / S), sa));
+  }
+  KMP_CUDA(cudaMemcpyAsync(target_out, d_target.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (favored_out != nullptr) {
+    KMP_CUDA(cudaMemcpyAsync(favored_out, d_fav.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  d_target.release();
+  d_fav.release();
+  return KMP_OK;
+}
+
+int kmp_lp_free_scratch(kmp_lp_handle *h) {
+  if (h == nullptr) {
+    return KMP_OK;
+  }
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->label.release();
+  h->favored.release();
+  h->communities.release();
+  h->weight.release();
+  h->maxw.release();
+  h->minw.release();
+  h->active.release();
+  h->mv_u.release();
+  h->mv_t.release();
+  h->cslot.release();
+  h->slotmap.release();
+  h->acc.release();
+  h->incoming.release();
+  h->chist.release();
+  h->hist.release();
+  h->jmin.release();
+  h->out_cur.release();
+  h->out_delta.release();
+  h->ohist.release();
+  h->ojmin.release();
+  h->ctr32.release();
+  h->ctr64.release();
+  h->hub_keys.release();
+  h->hub_vals.release();
+  h->cub_tmp.release();
+  h->pairs_a.release();
+  h->pairs_b.release();
+  h->slot_state_clean = false;
+  return KMP_OK;
+}
+
+int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out) {
+  if (h == nullptr || !h->have_graph || cut_out == nullptr || h->label.p == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  KMP_CUDA(h->ctr64.ensure(8));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 4, 0, sizeof(unsigned long long), h->stream));
+  k_edge_cut<<<grid_for(static_cast<uint64_t>(h->n) * 32, 256), 256, 0, h->stream>>>(h->n, h->xadj, h->adjncy, h->adjwgt,
+                                                                                      h->label.p, h->ctr64.p + 4);
+  unsigned long long c = 0;
+  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 4, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  *cut_out = static_cast<int64_t>(c / 2); // metrics.cc:51-52
+  return KMP_OK;
+}
+
+} // extern "C"

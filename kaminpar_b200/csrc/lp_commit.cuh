@@ -1,0 +1,264 @@
+// Commit kernels: resolve the proposals of one sub-round deterministically (DESIGN.md "commit
+// rule"), apply the accepted moves and re-activate neighbourhoods.
+//
+// They replace the reference's immediate, racy move (label_propagation.h:817-841 try_node_move,
+// :2139-2152 move_cluster_weight, partitioned_graph.h:397-428 move_block_weight) by an
+// order-independent rule: proposals into a target are accepted by ladder level
+// lvl(u) = min(clz(prio(u)), 15) from the top level downwards as long as the target's weight limit
+// holds; with several passes the weight of accepted departures is credited.
+#pragma once
+
+#include "lp_device.cuh"
+
+namespace kmp {
+
+struct CommitArgs {
+  // graph
+  const uint32_t *__restrict__ xadj;
+  const uint32_t *__restrict__ adjncy;
+  const int32_t *__restrict__ vwgt; // nullable
+  // state
+  uint32_t *__restrict__ label;
+  int32_t *__restrict__ weight;       // [n] or [k]
+  const int32_t *__restrict__ max_w;  // refiner [k]
+  const int32_t *__restrict__ min_w;  // refiner [k], nullable
+  uint8_t *__restrict__ active;
+  int32_t max_cluster_weight;
+  uint32_t k;
+  // proposals
+  const uint32_t *__restrict__ mv_u;
+  const uint32_t *__restrict__ mv_t;
+  uint8_t *__restrict__ acc; // 0 rejected/pending, 1 accepted, 2 contended-pending (clusterer)
+  const uint32_t *__restrict__ mover_count;
+  uint32_t base_commit;
+  // clusterer
+  int32_t *__restrict__ incoming; // [n]
+  uint32_t *__restrict__ slotmap; // [n], kEmpty when unused
+  uint32_t *__restrict__ cslot;   // [movers]
+  int32_t *__restrict__ chist;    // [movers][16], zero when unused
+  // refiner
+  int32_t *__restrict__ hist;  // [k][16]  weight per (target, level); becomes suffix sums (cum)
+  int32_t *__restrict__ jmin;  // [k]
+  int32_t *__restrict__ out_cur;   // [k] credited departures (complete)
+  int32_t *__restrict__ out_delta; // [k] departures accepted in the running pass
+  int32_t *__restrict__ ohist; // [k][16] source-side ladder (min weights)
+  int32_t *__restrict__ ojmin; // [k]
+  // results
+  uint32_t *__restrict__ moved_count;
+};
+
+__device__ __forceinline__ int32_t node_weight(const CommitArgs &a, uint32_t u) {
+  return a.vwgt != nullptr ? a.vwgt[u] : 1;
+}
+
+// ---- clusterer ----------------------------------------------------------------------------------
+// (1) uncontended targets accept everything; contended ones get a slot and a level histogram
+__global__ void commit_cluster_classify(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    if (a.weight[t] + a.incoming[t] <= a.max_cluster_weight) {
+      a.acc[i] = 1;
+    } else {
+      const uint32_t prev = atomicCAS(&a.slotmap[t], kEmpty, i);
+      const uint32_t slot = prev == kEmpty ? i : prev;
+      a.cslot[i] = slot;
+      const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+      atomicAdd(&a.chist[static_cast<size_t>(slot) * kLadderLevels + lvl], node_weight(a, u));
+      a.acc[i] = 2;
+    }
+  }
+}
+// (2) contended proposals: accept iff level >= jmin(target)
+__global__ void commit_cluster_decide(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    if (a.acc[i] != 2) {
+      continue;
+    }
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    const int32_t *h = a.chist + static_cast<size_t>(a.cslot[i]) * kLadderLevels;
+    const int32_t w_t = a.weight[t];
+    int32_t cum = 0;
+    int jm = kLadderLevels; // none
+#pragma unroll
+    for (int j = kLadderLevels - 1; j >= 0; --j) {
+      cum += h[j];
+      if (w_t + cum <= a.max_cluster_weight) {
+        jm = j; // feasible at level j; keep lowering while it still fits (cum is monotone)
+      }
+    }
+    const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+    a.acc[i] = static_cast<int>(lvl) >= jm ? 1 : 0;
+  }
+}
+
+// ---- refiner ------------------------------------------------------------------------------------
+// suffix sums of the level histograms + reset of the pass state (k threads)
+__global__ void commit_refine_prepare(const CommitArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.k) {
+    return;
+  }
+  int32_t cum = 0;
+  for (int j = kLadderLevels - 1; j >= 0; --j) {
+    cum += a.hist[b * kLadderLevels + j];
+    a.hist[b * kLadderLevels + j] = cum;
+  }
+  a.out_cur[b] = 0;
+  a.out_delta[b] = 0;
+}
+// jmin per block for the running pass; folds the previous pass' departures into out_cur (k threads)
+__global__ void commit_refine_jmin(const CommitArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.k) {
+    return;
+  }
+  const int32_t credit = a.out_cur[b] + a.out_delta[b];
+  a.out_cur[b] = credit;
+  a.out_delta[b] = 0;
+  int jm = kLadderLevels;
+  for (int j = 0; j < kLadderLevels; ++j) {
+    if (a.weight[b] + a.hist[b * kLadderLevels + j] - credit <= a.max_w[b]) {
+      jm = j;
+      break;
+    }
+  }
+  a.jmin[b] = jm;
+}
+__global__ void commit_refine_decide(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    if (a.acc[i] != 0) {
+      continue;
+    }
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+    if (static_cast<int>(lvl) >= a.jmin[t]) {
+      a.acc[i] = 1;
+      atomicAdd(&a.out_delta[a.label[u]], node_weight(a, u));
+    }
+  }
+}
+// source-side ladder for min block weights
+__global__ void commit_refine_ohist(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    if (a.acc[i] == 1) {
+      const uint32_t u = a.mv_u[i];
+      const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+      atomicAdd(&a.ohist[a.label[u] * kLadderLevels + lvl], node_weight(a, u));
+    }
+  }
+}
+__global__ void commit_refine_ojmin(const CommitArgs a) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.k) {
+    return;
+  }
+  int32_t cum[kLadderLevels];
+  int32_t c = 0;
+  for (int j = kLadderLevels - 1; j >= 0; --j) {
+    c += a.ohist[b * kLadderLevels + j];
+    cum[j] = c;
+    a.ohist[b * kLadderLevels + j] = 0; // reset for the next sub-round
+  }
+  int jm = kLadderLevels;
+  for (int j = 0; j < kLadderLevels; ++j) {
+    if (a.weight[b] - cum[j] >= a.min_w[b]) {
+      jm = j;
+      break;
+    }
+  }
+  a.ojmin[b] = jm;
+}
+__global__ void commit_refine_othin(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    if (a.acc[i] == 1) {
+      const uint32_t u = a.mv_u[i];
+      const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+      if (static_cast<int>(lvl) < a.ojmin[a.label[u]]) {
+        a.acc[i] = 0;
+      }
+    }
+  }
+}
+// reset the refiner histograms after the sub-round (k*16 threads)
+__global__ void commit_refine_reset(const CommitArgs a) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.k * kLadderLevels) {
+    a.hist[i] = 0;
+  }
+}
+
+// ---- apply (both modes): weights, labels, scratch clean-up -----------------------------------
+template <int MODE> __global__ void commit_apply(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  uint32_t moved = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    const uint8_t acc = a.acc[i];
+    if (MODE == 0) {
+      a.incoming[t] = 0; // every proposer of t writes the same value
+      if (a.slotmap[t] == i) { // slot owner cleans the contended-target scratch
+        int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
+#pragma unroll
+        for (int j = 0; j < kLadderLevels; ++j) {
+          h[j] = 0;
+        }
+        a.slotmap[t] = kEmpty;
+      }
+    }
+    if (acc == 1) {
+      const int32_t w = node_weight(a, u);
+      const uint32_t from = a.label[u];
+      atomicAdd(&a.weight[t], w);
+      atomicSub(&a.weight[from], w);
+      a.label[u] = t;
+      ++moved;
+    } else {
+      a.active[u] = 1; // rejected proposals retry in the next round
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    moved += __shfl_xor_sync(kFull, moved, o);
+  }
+  if ((threadIdx.x & 31) == 0 && moved != 0) {
+    atomicAdd(a.moved_count, moved);
+  }
+}
+
+// ---- activate neighbours of moved vertices (label_propagation.h:848-870) ----------------------
+// one warp per accepted proposal
+__global__ void commit_activate(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < cnt; i += nwarps) {
+    if (a.acc[i] != 1) {
+      continue;
+    }
+    const uint32_t u = a.mv_u[i];
+    const uint32_t beg = a.xadj[u];
+    const uint32_t end = a.xadj[u + 1];
+    for (uint32_t e = beg + lane; e < end; e += 32) {
+      a.active[a.adjncy[e]] = 1;
+    }
+  }
+}
+// acc[] must start at 0 for the refiner's multi-pass decide; clear it and the counters
+__global__ void commit_begin(uint8_t *acc, const uint32_t *mover_count) {
+  const uint32_t cnt = *mover_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    acc[i] = 0;
+  }
+}
+__global__ void reset_u32(uint32_t *p) { *p = 0; }
+
+} // namespace kmp

@@ -1,0 +1,477 @@
+// The LP sweep kernels: one kernel family per degree group of the sync schedule.
+//
+//   group 0 (deg 1..7)    sweep_thread : one thread per vertex, neighbour labels in registers
+//   group 1 (deg 8..31)   sweep_warp   : one warp per vertex, duplicates merged with match.any
+//   group 2 (deg 32..255) sweep_warp_hash : one warp per vertex, per-warp shared-memory hash map
+//   group 3 (deg >= 256)  sweep_block  : one CTA per vertex, CTA-wide shared-memory hash map or a
+//                                        global-memory table for very large neighbourhoods
+//
+// Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
+// rating[label[v]] += w(u,v) over adj(u) (:487-505), clear active[u] (:507-508), select
+// (lp_clusterer.cc:181-250 / lp_refiner.cc:151-245) and -- instead of moving immediately
+// (try_node_move :817-841) -- emit a proposal (u, target) that the commit kernels resolve.
+#pragma once
+
+#include "lp_device.cuh"
+
+namespace kmp {
+
+// ---- proposal emission --------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void emit_proposal(const SweepArgs &a, uint32_t idx, uint32_t u, uint32_t target,
+                                              int32_t uw) {
+  a.mv_u[idx] = u;
+  a.mv_t[idx] = target;
+  if (MODE == 0) {
+    atomicAdd(&a.incoming[target], uw);
+  } else {
+    const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+    atomicAdd(&a.hist[target * kLadderLevels + lvl], uw);
+  }
+}
+
+__device__ __forceinline__ void block_count_flush(const SweepArgs &a, unsigned long long edges,
+                                                  unsigned long long nodes) {
+  // warp-level then one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    edges += __shfl_xor_sync(kFull, edges, o);
+    nodes += __shfl_xor_sync(kFull, nodes, o);
+  }
+  if ((threadIdx.x & 31) == 0 && nodes != 0) {
+    atomicAdd(&a.counters[0], edges);
+    atomicAdd(&a.counters[1], nodes);
+  }
+}
+
+// ================================================================================================
+// group 0: thread per vertex, deg <= 7 (also used for any deg <= kMaxDeg)
+// ================================================================================================
+template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
+  constexpr int D = 7;
+  unsigned long long edges = 0, nodes = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // the loop bound is rounded up to a full warp so that all lanes reach the ballots
+  const uint32_t bound = (a.list_size + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += stride) {
+    bool proposes = false;
+    uint32_t u = 0, target = 0;
+    int32_t uw = 1;
+    if (i < a.list_size) {
+      u = a.list[i];
+      const bool is_active = a.active == nullptr || a.active[u] != 0;
+      if (is_active) {
+        const uint32_t beg = a.xadj[u];
+        uint32_t deg = a.xadj[u + 1] - beg;
+        if (deg > a.max_num_neighbors) {
+          deg = a.max_num_neighbors;
+        }
+        const uint32_t own = a.label[u];
+        uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+        const int32_t own_w = a.weight[own];
+        edges += deg;
+        nodes += 1;
+        if (a.active != nullptr) {
+          a.active[u] = 0;
+        }
+        bool skip = false;
+        if (MODE == 1) {
+          const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+          skip = (own_w - uw) < mn; // lp_refiner.cc:160-162
+        }
+        uint32_t keys[D];
+        int32_t ws[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          keys[j] = kEmpty;
+          ws[j] = 0;
+          if (!skip && j < static_cast<int>(deg)) {
+            const uint32_t v = a.adjncy[beg + j];
+            bool ok = true;
+            if (MODE == 1 && a.communities != nullptr) {
+              ok = a.communities[u] == a.communities[v];
+            }
+            if (ok) {
+              keys[j] = a.label[v];
+              ws[j] = EW ? a.adjwgt[beg + j] : 1;
+            }
+          }
+        }
+        const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+        Cand best = cand_none(), fav = cand_none();
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          if (keys[j] != kEmpty) {
+            bool rep = true;
+            int32_t rating = 0;
+#pragma unroll
+            for (int q = 0; q < D; ++q) {
+              const bool same = keys[q] == keys[j];
+              rating += same ? ws[q] : 0;
+              if (q < j && same) {
+                rep = false;
+              }
+            }
+            if (rep) {
+              Cand f;
+              const Cand c = eval_candidate<MODE>(a, u, own, uw, own_w, keys[j], rating, store_fav, f);
+              if (cand_better<MODE>(c, best)) {
+                best = c;
+              }
+              if (MODE == 0 && cand_better<0>(f, fav)) {
+                fav = f;
+              }
+            }
+          }
+        }
+        proposes = finish_vertex<MODE>(a, u, own, store_fav, best, fav, target);
+      }
+    }
+    const unsigned ballot = __ballot_sync(kFull, proposes);
+    if (ballot != 0) {
+      const int lane = threadIdx.x & 31;
+      uint32_t base = 0;
+      if (lane == 0) {
+        base = atomicAdd(a.mover_count, static_cast<uint32_t>(__popc(ballot)));
+      }
+      base = __shfl_sync(kFull, base, 0);
+      if (proposes) {
+        emit_proposal<MODE>(a, base + __popc(ballot & ((1u << lane) - 1u)), u, target, uw);
+      }
+    }
+  }
+  block_count_flush(a, edges, nodes);
+}
+
+// ================================================================================================
+// group 1: warp per vertex, deg <= 32, duplicates merged by match.any (no hash table)
+// ================================================================================================
+template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(const SweepArgs a) {
+  unsigned long long edges = 0, nodes = 0;
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < a.list_size; i += nwarps) {
+    const uint32_t u = a.list[i];
+    if (a.active != nullptr) { // lane 0 reads, so that its later active[u] = 0 cannot split the warp
+      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
+      act = __shfl_sync(kFull, act, 0);
+      if (act == 0) {
+        continue;
+      }
+    }
+    const uint32_t beg = a.xadj[u];
+    uint32_t deg = a.xadj[u + 1] - beg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t own = a.label[u];
+    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+    const int32_t own_w = a.weight[own];
+    if (lane == 0) {
+      edges += deg;
+      nodes += 1;
+      if (a.active != nullptr) {
+        a.active[u] = 0;
+      }
+    }
+    bool skip = false;
+    if (MODE == 1) {
+      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+      skip = (own_w - uw) < mn;
+    }
+    uint32_t key = kEmpty;
+    int32_t w = 0;
+    if (!skip && static_cast<uint32_t>(lane) < deg) {
+      const uint32_t v = a.adjncy[beg + lane];
+      bool ok = true;
+      if (MODE == 1 && a.communities != nullptr) {
+        ok = a.communities[u] == a.communities[v];
+      }
+      if (ok) {
+        key = a.label[v];
+        w = EW ? a.adjwgt[beg + lane] : 1;
+      }
+    }
+    const unsigned peers = __match_any_sync(kFull, key);
+    int32_t rating;
+    if (EW) {
+      // sum of w over the lanes holding the same key (uniform 32-step loop: every lane takes part in
+      // every shuffle, so no partial-mask collectives are needed)
+      rating = 0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int32_t wq = __shfl_sync(kFull, w, q);
+        rating += ((peers >> q) & 1u) ? wq : 0;
+      }
+    } else {
+      rating = __popc(peers);
+    }
+    const bool rep = (key != kEmpty) && (lane == __ffs(peers) - 1);
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand c = cand_none(), f = cand_none();
+    if (rep) {
+      c = eval_candidate<MODE>(a, u, own, uw, own_w, key, rating, store_fav, f);
+    }
+    const Cand best = warp_argmax<MODE>(kFull, c);
+    Cand fav = cand_none();
+    if (MODE == 0 && store_fav) {
+      fav = warp_argmax<0>(kFull, f);
+    }
+    if (lane == 0) {
+      uint32_t target;
+      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
+        const uint32_t idx = atomicAdd(a.mover_count, 1u);
+        emit_proposal<MODE>(a, idx, u, target, uw);
+      }
+    }
+  }
+  block_count_flush(a, edges, nodes);
+}
+
+// ================================================================================================
+// shared helpers for the hash-map kernels
+// ================================================================================================
+__device__ __forceinline__ uint32_t pow2_ceil(uint32_t x) { // x >= 1
+  return x <= 1 ? 1u : (1u << (32 - __clz(static_cast<int>(x - 1))));
+}
+
+// open addressing, linear probing; keys/vals may point to shared or global memory
+__device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_t mask, bool direct, uint32_t key,
+                                          int32_t w) {
+  uint32_t slot = direct ? key : (lowbias32(key) & mask);
+  while (true) {
+    const uint32_t prev = atomicCAS(&keys[slot], kEmpty, key);
+    if (prev == kEmpty || prev == key) {
+      atomicAdd(&vals[slot], w);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+// ================================================================================================
+// group 2: warp per vertex, per-warp shared-memory hash map (deg <= 256)
+// ================================================================================================
+constexpr int kWarpTableSlots = 512;
+constexpr int kWarpsPerBlockG2 = 8;
+
+template <int MODE, bool EW>
+__global__ void __launch_bounds__(kWarpsPerBlockG2 * 32) sweep_warp_hash(const SweepArgs a) {
+  __shared__ uint32_t s_keys[kWarpsPerBlockG2][kWarpTableSlots];
+  __shared__ int32_t s_vals[kWarpsPerBlockG2][kWarpTableSlots];
+  unsigned long long edges = 0, nodes = 0;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  uint32_t *keys = s_keys[wib];
+  int32_t *vals = s_vals[wib];
+  for (int s = lane; s < kWarpTableSlots; s += 32) {
+    keys[s] = kEmpty;
+    vals[s] = 0;
+  }
+  __syncwarp();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < a.list_size; i += nwarps) {
+    const uint32_t u = a.list[i];
+    if (a.active != nullptr) { // lane 0 reads, so that its later active[u] = 0 cannot split the warp
+      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
+      act = __shfl_sync(kFull, act, 0);
+      if (act == 0) {
+        continue;
+      }
+    }
+    const uint32_t beg = a.xadj[u];
+    uint32_t deg = a.xadj[u + 1] - beg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t own = a.label[u];
+    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+    const int32_t own_w = a.weight[own];
+    if (lane == 0) {
+      edges += deg;
+      nodes += 1;
+      if (a.active != nullptr) {
+        a.active[u] = 0;
+      }
+    }
+    bool skip = false;
+    if (MODE == 1) {
+      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+      skip = (own_w - uw) < mn;
+    }
+    const uint32_t distinct = deg < a.num_labels ? deg : a.num_labels;
+    const bool direct = a.num_labels <= static_cast<uint32_t>(kWarpTableSlots);
+    uint32_t cap = direct ? pow2_ceil(a.num_labels) : pow2_ceil(2 * distinct);
+    if (cap < 32) {
+      cap = 32;
+    }
+    const uint32_t mask = cap - 1;
+    if (!skip) {
+      for (uint32_t e = lane; e < deg; e += 32) {
+        const uint32_t v = a.adjncy[beg + e];
+        bool ok = true;
+        if (MODE == 1 && a.communities != nullptr) {
+          ok = a.communities[u] == a.communities[v];
+        }
+        if (ok) {
+          table_add(keys, vals, mask, direct, a.label[v], EW ? a.adjwgt[beg + e] : 1);
+        }
+      }
+    }
+    __syncwarp();
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand c = cand_none(), f = cand_none();
+    for (uint32_t s = lane; s < cap; s += 32) {
+      const uint32_t k = keys[s];
+      if (k != kEmpty) {
+        const int32_t r = vals[s];
+        keys[s] = kEmpty;
+        vals[s] = 0;
+        Cand ff;
+        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
+        if (cand_better<MODE>(cc, c)) {
+          c = cc;
+        }
+        if (MODE == 0 && cand_better<0>(ff, f)) {
+          f = ff;
+        }
+      }
+    }
+    __syncwarp();
+    const Cand best = warp_argmax<MODE>(kFull, c);
+    Cand fav = cand_none();
+    if (MODE == 0 && store_fav) {
+      fav = warp_argmax<0>(kFull, f);
+    }
+    if (lane == 0) {
+      uint32_t target;
+      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
+        const uint32_t idx = atomicAdd(a.mover_count, 1u);
+        emit_proposal<MODE>(a, idx, u, target, uw);
+      }
+    }
+  }
+  block_count_flush(a, edges, nodes);
+}
+
+// ================================================================================================
+// group 3: CTA per vertex (deg >= 256): CTA-wide shared hash map, global table for huge hubs
+// ================================================================================================
+constexpr int kBlockTableSlots = 8192; // 64 KiB of dynamic shared memory
+constexpr int kBlockThreadsG3 = 512;
+
+template <int MODE, bool EW> __global__ void __launch_bounds__(kBlockThreadsG3) sweep_block(const SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_keys = reinterpret_cast<uint32_t *>(smem_raw);
+  int32_t *s_vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kBlockTableSlots);
+  __shared__ Cand s_best[kBlockThreadsG3 / 32];
+  __shared__ Cand s_fav[kBlockThreadsG3 / 32];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int wib = tid >> 5;
+  for (int s = tid; s < kBlockTableSlots; s += kBlockThreadsG3) {
+    s_keys[s] = kEmpty;
+    s_vals[s] = 0;
+  }
+  __syncthreads();
+  unsigned long long edges = 0, nodes = 0;
+  for (uint32_t i = blockIdx.x; i < a.list_size; i += gridDim.x) {
+    const uint32_t u = a.list[i];
+    if (a.active != nullptr && a.active[u] == 0) {
+      continue; // uniform across the CTA
+    }
+    const uint32_t beg = a.xadj[u];
+    uint32_t deg = a.xadj[u + 1] - beg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t own = a.label[u];
+    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+    const int32_t own_w = a.weight[own];
+    bool skip = false;
+    if (MODE == 1) {
+      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+      skip = (own_w - uw) < mn;
+    }
+    const uint32_t distinct = deg < a.num_labels ? deg : a.num_labels;
+    const bool direct = a.num_labels <= static_cast<uint32_t>(kBlockTableSlots);
+    uint32_t cap = direct ? pow2_ceil(a.num_labels) : pow2_ceil(2 * distinct);
+    if (cap < 32) {
+      cap = 32;
+    }
+    uint32_t *keys = s_keys;
+    int32_t *vals = s_vals;
+    if (cap > static_cast<uint32_t>(kBlockTableSlots)) { // huge hub: global table of this CTA
+      keys = a.hub_keys + static_cast<size_t>(blockIdx.x) * a.hub_stride;
+      vals = a.hub_vals + static_cast<size_t>(blockIdx.x) * a.hub_stride;
+      if (cap > a.hub_stride) {
+        cap = a.hub_stride; // hub_stride = pow2_ceil(2 * max degree) >= needed
+      }
+    }
+    const uint32_t mask = cap - 1;
+    if (!skip) {
+      for (uint32_t e = tid; e < deg; e += kBlockThreadsG3) {
+        const uint32_t v = a.adjncy[beg + e];
+        bool ok = true;
+        if (MODE == 1 && a.communities != nullptr) {
+          ok = a.communities[u] == a.communities[v];
+        }
+        if (ok) {
+          table_add(keys, vals, mask, direct, a.label[v], EW ? a.adjwgt[beg + e] : 1);
+        }
+      }
+    }
+    __syncthreads();
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand c = cand_none(), f = cand_none();
+    for (uint32_t s = tid; s < cap; s += kBlockThreadsG3) {
+      const uint32_t k = keys[s];
+      if (k != kEmpty) {
+        const int32_t r = vals[s];
+        keys[s] = kEmpty;
+        vals[s] = 0;
+        Cand ff;
+        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
+        if (cand_better<MODE>(cc, c)) {
+          c = cc;
+        }
+        if (MODE == 0 && cand_better<0>(ff, f)) {
+          f = ff;
+        }
+      }
+    }
+    const Cand wb = warp_argmax<MODE>(kFull, c);
+    const Cand wf = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
+    if (lane == 0) {
+      s_best[wib] = wb;
+      s_fav[wib] = wf;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      Cand best = cand_none(), fav = cand_none();
+      for (int q = 0; q < kBlockThreadsG3 / 32; ++q) {
+        if (cand_better<MODE>(s_best[q], best)) {
+          best = s_best[q];
+        }
+        if (MODE == 0 && cand_better<0>(s_fav[q], fav)) {
+          fav = s_fav[q];
+        }
+      }
+      edges += deg;
+      nodes += 1;
+      if (a.active != nullptr) {
+        a.active[u] = 0;
+      }
+      uint32_t target;
+      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
+        const uint32_t idx = atomicAdd(a.mover_count, 1u);
+        emit_proposal<MODE>(a, idx, u, target, uw);
+      }
+    }
+    __syncthreads(); // table fully reset and s_best consumed before the next vertex
+  }
+  block_count_flush(a, edges, nodes);
+}
+
+} // namespace kmp
