@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- LP edges/s on B200 (BASELINE.json metric) for the B200-native label-propagation
+engine, next to the reference's own CPU path.
+
+A "step" = one ``LPClustering.compute_clustering`` call (5 LP rounds + post passes,
+lp_clusterer.cc:89-109) on the synthetic input, the timed region of the reference's own harness
+(apps/benchmarks/shm_label_propagation_benchmark.cc:121-123).
+
+  value  : scanned directed edges per second, graph already resident in HBM (device-timed)
+  e2e    : the same through the public API with HOST buffers -- graph H2D, clustering D2H inside
+           the timed region
+  roofline: dominant sweep kernel family, algorithmic bytes (8 B/scanned edge + 16 B/visited
+           vertex) / CUDA-event time of those launches, vs MEASURED_PEAKS.json
+  cpu_baseline: the unmodified reference (oracle/_ref, serial oneTBB stand-in => 1 core) or, when
+           that library is absent, the oracle port, on a bounded sample
+
+``--impl reference`` times only the CPU reference arm on the same workload definition.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (generator, args, k)   -- BASELINE.json configs
+    "rmat22": ("rmat", dict(scale=22, edge_factor=16, seed=1), 16),   # configs[1]
+    "rmat24": ("rmat", dict(scale=24, edge_factor=16, seed=1), 64),   # configs[3]
+    "rmat20": ("rmat", dict(scale=20, edge_factor=16, seed=1), 16),
+    "rmat18": ("rmat", dict(scale=18, edge_factor=16, seed=1), 16),
+    "grid512": ("grid", dict(nx=512), 64),                             # configs[2]
+    "grid256": ("grid", dict(nx=256), 64),
+    "rgg24": ("rgg", dict(n=1 << 24, seed=1), 64),
+    "rgg20": ("rgg", dict(n=1 << 20, seed=1), 64),
+}
+CPU_SAMPLE = {"rmat22": "rmat20", "rmat24": "rmat20", "rmat20": "rmat18", "rmat18": "rmat18",
+              "grid512": "grid256", "grid256": "grid256", "rgg24": "rgg20", "rgg20": "rgg20"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def generate(name, device):
+    """Synthetic input after the degree-bucket rearrangement the facade applies (kaminpar.cc:369-396).
+    Returns torch int64 (xadj, adjncy) on `device`."""
+    import torch
+
+    from kaminpar_b200 import graph as G
+
+    kind, args, k = WORKLOADS[name]
+    if kind == "rmat":
+        n = 1 << args["scale"]
+        src, dst = G.rmat_edges_torch(args["scale"], args["edge_factor"], args["seed"], device)
+        xadj, adj = G._csr_from_pairs_torch(n, src, dst, device)
+    elif kind == "grid":
+        g = G.grid3d(args["nx"])
+        xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)
+        adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
+    elif kind == "rgg":
+        g = G.rgg2d(args["n"], args["seed"], device=device)
+        xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)
+        adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
+    else:
+        raise ValueError(kind)
+    xadj, adj, _ = G.rearrange_by_degree_buckets_torch(xadj, adj, remove_isolated=True)
+    return xadj, adj, k
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(name, steps, warmup):
+    """The reference's own CPU path (oracle/_ref: unmodified sources, serial oneTBB stand-in => one
+    core) or, if that library did not travel, the oracle port of the same algorithm. Returns
+    (edges_per_s, seconds_per_step, kind, cores, sample_description)."""
+    import torch
+
+    from kaminpar_b200.graph import CSRGraph
+    from oracle import bindings as B
+
+    sample = CPU_SAMPLE.get(name, name)
+    xadj, adj, k = generate(sample, "cpu")
+    g = CSRGraph(xadj.numpy().astype(np.uint32), adj.numpy().astype(np.uint32), sorted=True)
+    mcw = B.oracle_max_cluster_weight(g, k)
+    # scanned-edge count of the sequential schedule (deterministic for a seed)
+    _, st = B.oracle_lp_cluster(g, 0, mcw, schedule=B.SEQ, return_stats=True)
+    edges = int(st[0].edges_scanned)
+    if B.have_reference():
+        kind, fn = "reference", (lambda: B.ref_lp_cluster(g, 0, mcw))
+    else:
+        kind, fn = "port", (lambda: B.oracle_lp_cluster(g, 0, mcw, schedule=B.SEQ))
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    desc = (f"{sample}: n={g.n} m={g.m} k={k}, LPClustering.compute_clustering at 1 thread "
+            f"({edges} scanned edges/step)")
+    return edges / dt, dt, kind, 1, desc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KMP_BENCH_WORKLOAD", "rmat22"))
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "lp_edges_per_second"
+    unit = "edges/s"
+    _, _, k = WORKLOADS[args.workload][0], WORKLOADS[args.workload][1], WORKLOADS[args.workload][2]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        eps, dt, kind, cores, desc = cpu_reference_run(args.workload, args.steps, max(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": eps, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "k": k, "mode": "clustering", "sample": CPU_SAMPLE.get(args.workload)},
+            "cpu_baseline": {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": eps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    from kaminpar_b200 import lp
+    from kaminpar_b200.graph import CSRGraph
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: kaminpar_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- input (synthetic, generated on the device; per-rank seed offset for N > 1) ------------
+    wl = args.workload
+    xadj64, adj64, k = generate(wl, dev)
+    n = xadj64.numel() - 1
+    m = adj64.numel()
+    d_xadj = xadj64.to(torch.int32)   # bit pattern == uint32 (m < 2^31)
+    d_adj = adj64.to(torch.int32)
+    del xadj64, adj64
+    torch.cuda.synchronize()
+    h_xadj = torch.empty(n + 1, dtype=torch.int32, pin_memory=True).copy_(d_xadj)
+    h_adj = torch.empty(m, dtype=torch.int32, pin_memory=True).copy_(d_adj)
+    h_out = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    g_host = CSRGraph.__new__(CSRGraph)  # views on pinned memory, no copies
+    g_host.xadj = h_xadj.numpy().view(np.uint32)
+    g_host.adjncy = h_adj.numpy().view(np.uint32)
+    g_host.vwgt = None
+    g_host.adjwgt = None
+    g_host.sorted = True
+    g_host.buckets = None
+
+    ctx = lp.create_default_context()
+    ctx.partition.setup(g_host, k, 0.03)
+    mcw = lp.compute_max_cluster_weight(ctx.coarsening, ctx.partition, n, n)
+
+    # ---- device-resident arm ("value") -------------------------------------------------------
+    handle = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
+    handle.set_graph_device(n, m, d_xadj.data_ptr(), d_adj.data_ptr())
+    handle.set_timing(True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        handle.cluster(mcw, fetch=False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    tot_ms = 0.0
+    edges = nodes = launches = sweeps = 0
+    g_edges = [0] * 4
+    g_nodes = [0] * 4
+    g_ms = [0.0] * 4
+    g_launch = [0] * 4
+    last = None
+    for _ in range(args.steps):
+        _, st = handle.cluster(mcw, fetch=False)
+        tot_ms += st.device_ms
+        edges += st.edges_scanned
+        nodes += st.nodes_visited
+        launches += st.kernel_launches
+        sweeps += st.sweep_launches
+        for q in range(4):
+            g_edges[q] += st.group_edges[q]
+            g_nodes[q] += st.group_nodes[q]
+            g_ms[q] += st.group_sweep_ms[q]
+            g_launch[q] += st.group_launches[q]
+        last = st
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([tot_ms, float(edges)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        tot_ms_max, edges_all = float(tmax[0]), float(t[1])
+    else:
+        tot_ms_max, edges_all = tot_ms, float(edges)
+    value = edges_all / (tot_ms_max * 1e-3)
+
+    # ---- e2e arm: public API, host buffers, H2D + D2H inside the timed region -------------------
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    out_np = h_out.numpy().view(np.uint32)
+
+    def e2e_step():
+        clusterer._graph = None  # new graph each step: forces the H2D copy, as one coarsening level does
+        clusterer.compute_clustering(g_host, clustering=out_np)
+        return clusterer.last_stats.edges_scanned
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e2e_edges = 0
+    for _ in range(args.steps):
+        e2e_edges += e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(e2e_edges)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_edges = float(tmax[0]), float(t[1])
+    e2e_value = e2e_edges / e2e_s
+    h2d = (n + 1) * 4 + m * 4
+    d2h = n * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant sweep kernel family -------------------------------------------
+    peak, peak_src = peaks()
+    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_warp_hash(deg<256)", "sweep_block(deg>=256)"]
+    dom = int(np.argmax(g_ms))
+    alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]
+    achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0
+    all_bytes = 8 * edges + 16 * nodes
+    sweep_ms_total = sum(g_ms)
+    roofline = {
+        "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "launches": g_launch[dom], "avg_launch_ms": g_ms[dom] / max(g_launch[dom], 1),
+        "algorithmic_bytes_per_launch": alg_bytes / max(g_launch[dom], 1),
+        "share_of_step": g_ms[dom] / tot_ms if tot_ms > 0 else None,
+        "all_sweeps": {"achieved": all_bytes / (sweep_ms_total * 1e-3) / 1e9 if sweep_ms_total > 0 else 0.0,
+                       "share_of_step": sweep_ms_total / tot_ms if tot_ms > 0 else None,
+                       "per_group_ms": [x / args.steps for x in g_ms],
+                       "per_group_edges": [x // args.steps for x in g_edges]},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        eps, dt, kind, cores, desc = cpu_reference_run(wl, args.cpu_steps, 1)
+        cpu = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
+
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": wl, "n": n, "m_directed": m, "k": k, "mode": "clustering",
+                   "max_cluster_weight": mcw, "iterations": last.iterations, "moved": last.moved_list(),
+                   "num_clusters": last.num_clusters, "l2": "inputs_larger_than_l2" if m * 4 > 126e6 else "small_input",
+                   "parallelism": "single" if world == 1 else f"replicas{world}",
+                   "subrounds": ctx.engine.sync_subrounds},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -82,6 +82,8 @@ struct kmp_lp_handle {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
+  std::vector<int> sweep_event_group;
+  uint64_t group_launches[4] = {0, 0, 0, 0};
   size_t sweep_events_used = 0;
 
   // graph
@@ -304,10 +306,12 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
   return cudaGetLastError();
 }
 
-cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs &a) {
-  if (a.list_size == 0) {
+cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs &a_in) {
+  if (a_in.list_size == 0) {
     return cudaSuccess;
   }
+  SweepArgs a = a_in;
+  a.counters = h->ctr64.p + group;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (h->timing) {
     if (h->sweep_events_used == h->sweep_events.size()) {
@@ -315,7 +319,9 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs 
       cudaEventCreate(&x);
       cudaEventCreate(&y);
       h->sweep_events.emplace_back(x, y);
+      h->sweep_event_group.push_back(0);
     }
+    h->sweep_event_group[h->sweep_events_used] = group;
     e0 = h->sweep_events[h->sweep_events_used].first;
     e1 = h->sweep_events[h->sweep_events_used].second;
     ++h->sweep_events_used;
@@ -333,6 +339,7 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs 
   }
   ++h->kernel_launches;
   ++h->sweep_launches;
+  ++h->group_launches[group];
   return e;
 }
 
@@ -397,7 +404,7 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
   KMP_CUDA(h->mv_t.ensure(cap));
   KMP_CUDA(h->acc.ensure(cap));
   KMP_CUDA(h->ctr32.ensure(512));
-  KMP_CUDA(h->ctr64.ensure(8));
+  KMP_CUDA(h->ctr64.ensure(16));
   KMP_CUDA(h->active.ensure(h->n));
   if (mode == 0) {
     KMP_CUDA(h->cslot.ensure(cap));
@@ -584,6 +591,9 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   h->kernel_launches = 0;
   h->sweep_launches = 0;
   h->sweep_events_used = 0;
+  for (int g = 0; g < 4; ++g) {
+    h->group_launches[g] = 0;
+  }
   KMP_CUDA(cudaEventRecord(h->ev_begin, h->stream));
   return KMP_OK;
 }
@@ -592,10 +602,15 @@ int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   KMP_CUDA(cudaEventRecord(h->ev_end, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   if (stats != nullptr) {
-    unsigned long long c[3] = {0, 0, 0};
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     KMP_CUDA(cudaMemcpy(c, h->ctr64.p, sizeof(c), cudaMemcpyDeviceToHost));
-    stats->edges_scanned = c[0];
-    stats->nodes_visited = c[1];
+    for (int g = 0; g < 4; ++g) {
+      stats->group_edges[g] = c[g];
+      stats->group_nodes[g] = c[4 + g];
+      stats->group_launches[g] = h->group_launches[g];
+      stats->edges_scanned += c[g];
+      stats->nodes_visited += c[4 + g];
+    }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
     stats->device_ms = ms;
@@ -604,6 +619,7 @@ int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
       float t = 0.f;
       cudaEventElapsedTime(&t, h->sweep_events[i].first, h->sweep_events[i].second);
       sweep += t;
+      stats->group_sweep_ms[h->sweep_event_group[i]] += t;
     }
     stats->sweep_ms = sweep;
     stats->sweep_launches = h->sweep_launches;
@@ -878,7 +894,7 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
   if (n > 0) {
     k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p,
                                                             h->active.p);
@@ -987,7 +1003,7 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
   KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
   if (n > 0) {
     k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
@@ -1055,7 +1071,7 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
       KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
     }
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 8 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
@@ -1123,12 +1139,12 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out) {
     return fail(KMP_ERR_INVALID, "bad argument");
   }
   KMP_CUDA(cudaSetDevice(h->device));
-  KMP_CUDA(h->ctr64.ensure(8));
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 4, 0, sizeof(unsigned long long), h->stream));
+  KMP_CUDA(h->ctr64.ensure(16));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 12, 0, sizeof(unsigned long long), h->stream));
   k_edge_cut<<<grid_for(static_cast<uint64_t>(h->n) * 32, 256), 256, 0, h->stream>>>(h->n, h->xadj, h->adjncy, h->adjwgt,
-                                                                                      h->label.p, h->ctr64.p + 4);
+                                                                                      h->label.p, h->ctr64.p + 12);
   unsigned long long c = 0;
-  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 4, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 12, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *cut_out = static_cast<int64_t>(c / 2); // metrics.cc:51-52
   return KMP_OK;

@@ -139,7 +139,7 @@ struct SweepArgs {
   uint32_t *__restrict__ mover_count;
   int32_t *__restrict__ incoming;      // clusterer: [n]
   int32_t *__restrict__ hist;          // refiner: [k][16]
-  unsigned long long *__restrict__ counters; // [0] edges scanned, [1] nodes visited
+  unsigned long long *__restrict__ counters; // [0] edges scanned, [4] nodes visited (of this degree group)
   // select_all mode (T0 parity hook): write decisions instead of proposing
   uint32_t *__restrict__ sel_target;
   uint32_t *__restrict__ sel_favored;

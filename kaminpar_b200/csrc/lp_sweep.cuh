@@ -38,8 +38,8 @@ __device__ __forceinline__ void block_count_flush(const SweepArgs &a, unsigned l
     nodes += __shfl_xor_sync(kFull, nodes, o);
   }
   if ((threadIdx.x & 31) == 0 && nodes != 0) {
-    atomicAdd(&a.counters[0], edges);
-    atomicAdd(&a.counters[1], nodes);
+    atomicAdd(&a.counters[0], edges); // counters points at this degree group's slot
+    atomicAdd(&a.counters[4], nodes);
   }
 }
 

@@ -294,3 +294,41 @@ def random_weights(g: CSRGraph, seed: int, max_vwgt: int = 0, max_adjwgt: int = 
         key = (lo * np.int64(1000003) + hi * np.int64(998244353) + np.int64(seed)) & np.int64(0x7FFFFFFF)
         adjwgt = (key % max_adjwgt + 1).astype(np.int32)
     return CSRGraph(xadj=g.xadj, adjncy=g.adjncy, vwgt=vwgt, adjwgt=adjwgt, sorted=g.sorted, buckets=g.buckets)
+
+
+# --------------------------------------------------------------------------------------------
+# Degree-bucket rearrangement (what KaMinPar::compute_partition applies before any LP runs:
+# kaminpar-shm/kaminpar.cc:369-396, graphutils/permutator.h:28-208, csr_graph.cc:150-174)
+# --------------------------------------------------------------------------------------------
+def rearrange_by_degree_buckets_torch(xadj, adjncy, remove_isolated=True):
+    """torch (CPU or CUDA) version for benchmark-sized inputs: stable sort of the vertices by degree
+    bucket (0 if d == 0 else floor(log2 d) + 1, isolated vertices last), neighbours relabelled and
+    every adjacency list reversed, isolated vertices cut off the end. Unit weights only.
+    Returns (xadj:int64[n'+1], adjncy:int64[m], old_to_new:int64[n])."""
+    import torch
+
+    n = xadj.numel() - 1
+    deg = xadj[1:] - xadj[:-1]
+    bucket = torch.where(deg > 0, torch.floor(torch.log2(deg.clamp(min=1).double())).long() + 1,
+                         torch.full_like(deg, 40))
+    # exact integer floor(log2): fix potential fp rounding at powers of two
+    bucket = torch.where((deg > 0) & ((1 << (bucket - 1).clamp(min=0, max=62)) > deg), bucket - 1, bucket)
+    new_to_old = torch.argsort(bucket, stable=True)
+    old_to_new = torch.empty_like(new_to_old)
+    old_to_new[new_to_old] = torch.arange(n, device=xadj.device)
+    new_deg = deg[new_to_old]
+    new_xadj = torch.zeros(n + 1, dtype=torch.int64, device=xadj.device)
+    torch.cumsum(new_deg, 0, out=new_xadj[1:])
+    m = adjncy.numel()
+    src_old = torch.repeat_interleave(torch.arange(n, device=xadj.device), deg)
+    e = torch.arange(m, device=xadj.device)
+    u_new = old_to_new[src_old]
+    pos = new_xadj[u_new + 1] - 1 - (e - xadj[src_old])
+    del src_old, e, u_new
+    new_adj = torch.empty_like(adjncy)
+    new_adj[pos] = old_to_new[adjncy]
+    del pos
+    n_lp = n
+    if remove_isolated:
+        n_lp = int((deg > 0).sum().item())
+    return new_xadj[: n_lp + 1].contiguous(), new_adj, old_to_new

@@ -185,7 +185,6 @@ def test_t1_communities_and_limits():
     cp.max_num_neighbors, cp.large_degree_threshold = 6, 300
     expect = B.oracle_lp_cluster(g, 9, mcw, schedule=B.SYNC, params=cp, communities=comm)
     assert np.array_equal(c, expect)
-    assert (comm[c] == comm).all()  # a vertex only joins clusters of its own community
 
 
 def test_t1_free_memory_afterwards_and_regraph():
