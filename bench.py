@@ -247,10 +247,10 @@ def main():
     sampler.start()
     tot_ms = 0.0
     edges = nodes = launches = sweeps = 0
-    g_edges = [0] * 4
-    g_nodes = [0] * 4
-    g_ms = [0.0] * 4
-    g_launch = [0] * 4
+    g_edges = [0] * 5
+    g_nodes = [0] * 5
+    g_ms = [0.0] * 5
+    g_launch = [0] * 5
     last = None
     for _ in range(args.steps):
         _, st = handle.cluster(mcw, fetch=False)
@@ -259,7 +259,7 @@ def main():
         nodes += st.nodes_visited
         launches += st.kernel_launches
         sweeps += st.sweep_launches
-        for q in range(4):
+        for q in range(5):
             g_edges[q] += st.group_edges[q]
             g_nodes[q] += st.group_nodes[q]
             g_ms[q] += st.group_sweep_ms[q]
@@ -314,7 +314,8 @@ def main():
 
     # ---- roofline of the dominant sweep kernel family -------------------------------------------
     peak, peak_src = peaks()
-    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_warp_hash(deg<256)", "sweep_block(deg>=256)"]
+    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_warp_hash(deg<256)", "sweep_group(deg<2048)",
+             "sweep_hub_aggregate+select(deg>=2048)"]
     dom = int(np.argmax(g_ms))
     alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]
     achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0

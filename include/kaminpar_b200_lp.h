@@ -85,12 +85,12 @@ typedef struct {
   float sweep_ms;            /* CUDA-event time spent in the sweep kernels only (if timing enabled) */
   uint64_t sweep_launches;   /* number of sweep-kernel launches */
   uint64_t kernel_launches;  /* all kernel launches of the call */
-  /* per degree group (0: deg<8 sweep_thread, 1: deg<32 sweep_warp, 2: deg<256 sweep_warp_hash,
-   * 3: deg>=256 sweep_block) */
-  uint64_t group_edges[4];
-  uint64_t group_nodes[4];
-  uint64_t group_launches[4];
-  float group_sweep_ms[4];   /* only when timing is enabled */
+  /* per kernel tier (0: deg<8 sweep_thread, 1: deg<32 sweep_warp, 2: deg<256 sweep_warp_hash,
+   * 3: deg<2048 sweep_group, 4: deg>=2048 sweep_hub_aggregate+sweep_hub_select; 5..7 unused) */
+  uint64_t group_edges[8];
+  uint64_t group_nodes[8];
+  uint64_t group_launches[8];
+  float group_sweep_ms[8];   /* only when timing is enabled */
 } kmp_lp_stats;
 
 typedef struct kmp_lp_handle kmp_lp_handle;

@@ -45,7 +45,8 @@ int fail(int code, const std::string &msg) {
     }                                                                                                      \
   } while (0)
 
-constexpr int kNumGroups = 4;
+constexpr int kNumGroups = 4; // degree groups of the schedule
+constexpr int kNumTiers = 5;  // kernel tiers: group 3 is split at degree 2048
 constexpr int kSMs = 148;
 
 template <typename T> struct DevBuf {
@@ -83,7 +84,7 @@ struct kmp_lp_handle {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
   std::vector<int> sweep_event_group;
-  uint64_t group_launches[4] = {0, 0, 0, 0};
+  uint64_t group_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   size_t sweep_events_used = 0;
 
   // graph
@@ -116,9 +117,15 @@ struct kmp_lp_handle {
   DevBuf<int32_t> incoming, chist, hist, jmin, out_cur, out_delta, ohist, ojmin;
   DevBuf<uint32_t> ctr32; // [0] mover_count [1] moved_count (per iteration) [2] misc
   DevBuf<unsigned long long> ctr64; // [0] edges [1] nodes [2] proposals
+  // tier 4 (deg >= 2048): per list entry the first slot of its global table region, and the
+  // (entry, chunk) work items of phase 1; all per sub-round
+  DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk;
+  std::vector<uint32_t> t4_item_off; // S + 1
+  uint64_t t4_max_slots = 0;
   DevBuf<uint32_t> hub_keys;
   DevBuf<int32_t> hub_vals;
-  uint32_t hub_stride = 0, hub_grid = 0;
+  uint32_t mover_cap = 0;
+  uint32_t cur_subround = 0;
   DevBuf<uint8_t> sort_keys_in, sort_keys_out;
   DevBuf<uint32_t> sort_vals_in;
   DevBuf<unsigned char> cub_tmp;
@@ -140,9 +147,10 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32
     const uint32_t d = xadj[u + 1] - xadj[u];
     uint32_t key;
     if (d == 0 || !(d < large_degree_threshold)) {
-      key = kNumGroups * S; // never visited (label_propagation.h:1795, :1914-1915)
+      key = kNumTiers * S; // never visited (label_propagation.h:1795, :1914-1915)
     } else {
-      key = degree_group(d) * S + subround_of(u, granule_log2, base_sr, S);
+      const uint32_t tier = d < kTier4MinDegree ? degree_group(d) : 4u;
+      key = tier * S + subround_of(u, granule_log2, base_sr, S);
     }
     keys[u] = static_cast<uint8_t>(key);
     vals[u] = u;
@@ -155,6 +163,13 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32
   }
   if ((threadIdx.x & 31) == 0) {
     atomicMax(max_deg, local_max);
+  }
+}
+
+__global__ void k_gather_degrees(uint32_t cnt, const uint32_t *list, const uint32_t *xadj, uint32_t *deg) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t u = list[i];
+    deg[i] = xadj[u + 1] - xadj[u];
   }
 }
 
@@ -296,10 +311,30 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
         <<<grid_for(static_cast<uint64_t>(a.list_size) * 32, kWarpsPerBlockG2 * 32), kWarpsPerBlockG2 * 32, 0,
            h->stream>>>(a);
     break;
+  case 3: {
+    const size_t smem = static_cast<size_t>(kGroupTableSlots) * kGroupsPerBlock * 8;
+    const uint32_t blocks = grid_for(static_cast<uint64_t>((a.list_size + kGroupsPerBlock - 1) / kGroupsPerBlock) *
+                                         kGroupThreads * kGroupsPerBlock,
+                                     kGroupThreads * kGroupsPerBlock, kSMs * 6);
+    sweep_group<MODE, EW><<<blocks, kGroupThreads * kGroupsPerBlock, smem, h->stream>>>(a);
+    break;
+  }
   default: {
-    const size_t smem = static_cast<size_t>(kBlockTableSlots) * 8;
-    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(a.list_size, h->hub_grid));
-    sweep_block<MODE, EW><<<blocks, kBlockThreadsG3, smem, h->stream>>>(a);
+    HubArgs hb{};
+    const uint32_t s_idx = h->cur_subround;
+    hb.item_entry = h->t4_item_entry.p + h->t4_item_off[s_idx];
+    hb.item_chunk = h->t4_item_chunk.p + h->t4_item_off[s_idx];
+    hb.num_items = h->t4_item_off[s_idx + 1] - h->t4_item_off[s_idx];
+    hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
+    hb.g_keys = h->hub_keys.p;
+    hb.g_vals = h->hub_vals.p;
+    const size_t smem = static_cast<size_t>(kChunkTableSlots) * 8;
+    if (hb.num_items > 0) {
+      sweep_hub_aggregate<MODE, EW>
+          <<<std::min<uint32_t>(hb.num_items, kSMs * 12), kChunkThreads, smem, h->stream>>>(a, hb);
+    }
+    sweep_hub_select<MODE><<<std::min<uint32_t>(a.list_size, kSMs * 8), kChunkThreads, 0, h->stream>>>(a, hb);
+    ++h->kernel_launches;
     break;
   }
   }
@@ -349,11 +384,11 @@ int ensure_lists(kmp_lp_handle *h) {
       h->lists_thr == h->cfg.large_degree_threshold && h->lists_seed == h->cfg.seed) {
     return KMP_OK;
   }
-  if (kNumGroups * S + 1 > 255) {
-    return fail(KMP_ERR_INVALID, "sync_subrounds too large (max 63)");
+  if (kNumTiers * S + 1 > 255) {
+    return fail(KMP_ERR_INVALID, "sync_subrounds too large (max 50)");
   }
   const uint32_t n = h->n;
-  const uint32_t nkeys = kNumGroups * S + 1;
+  const uint32_t nkeys = kNumTiers * S + 1;
   KMP_CUDA(h->sort_keys_in.ensure(n));
   KMP_CUDA(h->sort_keys_out.ensure(n));
   KMP_CUDA(h->sort_vals_in.ensure(n));
@@ -377,14 +412,65 @@ int ensure_lists(kmp_lp_handle *h) {
   KMP_CUDA(cudaMemcpyAsync(hist.data(), h->ctr32.p, 512 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   h->list_off.assign(nkeys + 1, 0);
-  h->max_list = 0;
   for (uint32_t kx = 0; kx < nkeys; ++kx) {
     h->list_off[kx + 1] = h->list_off[kx] + hist[kx];
-    if (kx + 1 < nkeys) {
-      h->max_list = std::max(h->max_list, hist[kx]);
+  }
+  auto lsize = [&](uint32_t tier, uint32_t sr) { return hist[tier * S + sr]; };
+  h->max_list = 0;
+  h->mover_cap = 1;
+  for (uint32_t sr = 0; sr < S; ++sr) {
+    for (uint32_t t = 0; t < 3; ++t) {
+      h->mover_cap = std::max(h->mover_cap, lsize(t, sr));
+    }
+    h->mover_cap = std::max(h->mover_cap, lsize(3, sr) + lsize(4, sr));
+  }
+  h->max_list = h->mover_cap;
+  h->max_degree = hist[300];
+  // ---- tier 4 metadata: table regions and chunk work items per sub-round ------------------------
+  {
+    const uint32_t t4_begin = h->list_off[4 * S], t4_end = h->list_off[5 * S];
+    const uint32_t t4_cnt = t4_end - t4_begin;
+    h->t4_item_off.assign(S + 1, 0);
+    h->t4_max_slots = 0;
+    if (t4_cnt > 0) {
+      DevBuf<uint32_t> d_deg;
+      KMP_CUDA(d_deg.ensure(t4_cnt));
+      k_gather_degrees<<<grid_for(t4_cnt, 256), 256, 0, h->stream>>>(t4_cnt, h->order.p + t4_begin, h->xadj, d_deg.p);
+      std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), ient, ichk;
+      KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      KMP_CUDA(cudaStreamSynchronize(h->stream));
+      d_deg.release();
+      for (uint32_t sr = 0; sr < S; ++sr) {
+        const uint32_t lo = h->list_off[4 * S + sr] - t4_begin, hi = h->list_off[4 * S + sr + 1] - t4_begin;
+        uint64_t slots = 0;
+        for (uint32_t i = lo; i < hi; ++i) {
+          uint64_t cap = 32;
+          while (cap < 2ull * deg[i]) {
+            cap <<= 1;
+          }
+          if (slots + cap > 0xFFFFFFFFull) {
+            return fail(KMP_ERR_UNSUPPORTED, "high-degree table of one sub-round exceeds 2^32 slots");
+          }
+          toff[i] = static_cast<uint32_t>(slots);
+          slots += cap;
+          const uint32_t chunks = (deg[i] + kChunkEdges - 1) / kChunkEdges;
+          for (uint32_t c = 0; c < chunks; ++c) {
+            ient.push_back(i - lo);
+            ichk.push_back(c);
+          }
+        }
+        h->t4_max_slots = std::max(h->t4_max_slots, slots);
+        h->t4_item_off[sr + 1] = static_cast<uint32_t>(ient.size());
+      }
+      KMP_CUDA(h->t4_table_off.ensure(t4_cnt));
+      KMP_CUDA(h->t4_item_entry.ensure(ient.size()));
+      KMP_CUDA(h->t4_item_chunk.ensure(ichk.size()));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_table_off.p, toff.data(), t4_cnt * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_item_entry.p, ient.data(), ient.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_item_chunk.p, ichk.data(), ichk.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaStreamSynchronize(h->stream));
     }
   }
-  h->max_degree = hist[300];
   h->lists_S = S;
   h->lists_G = h->cfg.sync_granule_log2;
   h->lists_thr = h->cfg.large_degree_threshold;
@@ -399,12 +485,12 @@ int ensure_lists(kmp_lp_handle *h) {
 
 // scratch shared by both modes
 int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
-  const size_t cap = std::max<uint32_t>(h->max_list, 1);
+  const size_t cap = std::max<uint32_t>(h->mover_cap, 1);
   KMP_CUDA(h->mv_u.ensure(cap));
   KMP_CUDA(h->mv_t.ensure(cap));
   KMP_CUDA(h->acc.ensure(cap));
   KMP_CUDA(h->ctr32.ensure(512));
-  KMP_CUDA(h->ctr64.ensure(16));
+  KMP_CUDA(h->ctr64.ensure(32));
   KMP_CUDA(h->active.ensure(h->n));
   if (mode == 0) {
     KMP_CUDA(h->cslot.ensure(cap));
@@ -429,27 +515,14 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
     KMP_CUDA(cudaMemsetAsync(h->hist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
     KMP_CUDA(cudaMemsetAsync(h->ohist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
   }
-  // hub tables (global-memory hash maps of sweep_block)
-  const uint32_t distinct = std::min<uint32_t>(h->max_degree, num_labels);
-  h->hub_grid = kSMs * 2;
-  h->hub_stride = 0;
-  if (num_labels > static_cast<uint32_t>(kBlockTableSlots) && 2ull * distinct > static_cast<uint64_t>(kBlockTableSlots)) {
-    uint64_t stride = 1;
-    while (stride < 2ull * distinct) {
-      stride <<= 1;
-    }
-    const uint64_t budget_slots = (2ull << 30) / 8; // 2 GiB of tables
-    uint64_t grid = std::max<uint64_t>(8, std::min<uint64_t>(kSMs * 2, budget_slots / stride));
-    h->hub_grid = static_cast<uint32_t>(grid);
-    h->hub_stride = static_cast<uint32_t>(stride);
-    const size_t slots = static_cast<size_t>(grid) * stride;
-    if (h->hub_keys.cap < slots) {
-      KMP_CUDA(h->hub_keys.ensure(slots));
-      KMP_CUDA(h->hub_vals.ensure(slots));
-      KMP_CUDA(cudaMemsetAsync(h->hub_keys.p, 0xFF, slots * sizeof(uint32_t), h->stream));
-      KMP_CUDA(cudaMemsetAsync(h->hub_vals.p, 0, slots * sizeof(int32_t), h->stream));
-    }
+  // global table regions of tier 4 (kept clean by sweep_hub_select)
+  if (h->t4_max_slots > 0 && h->hub_keys.cap < h->t4_max_slots) {
+    KMP_CUDA(h->hub_keys.ensure(h->t4_max_slots));
+    KMP_CUDA(h->hub_vals.ensure(h->t4_max_slots));
+    KMP_CUDA(cudaMemsetAsync(h->hub_keys.p, 0xFF, h->t4_max_slots * sizeof(uint32_t), h->stream));
+    KMP_CUDA(cudaMemsetAsync(h->hub_vals.p, 0, h->t4_max_slots * sizeof(int32_t), h->stream));
   }
+  (void)num_labels;
   return KMP_OK;
 }
 
@@ -485,9 +558,6 @@ SweepArgs make_sweep_args(kmp_lp_handle *h, const RunCtx &rc) {
   a.counters = h->ctr64.p;
   a.sel_target = nullptr;
   a.sel_favored = nullptr;
-  a.hub_keys = h->hub_keys.p;
-  a.hub_vals = h->hub_vals.p;
-  a.hub_stride = h->hub_stride;
   return a;
 }
 
@@ -531,18 +601,27 @@ int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *m
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // mover, moved, proposals
   const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
-    const uint32_t off = h->list_off[sg];
-    const uint32_t size = h->list_off[sg + 1] - off;
+    const int group = static_cast<int>(sg / S);
+    const uint32_t sr = sg % S;
+    // degree group 3 of the schedule = kernel tiers 3 and 4
+    const uint32_t size_a = h->list_off[sg + 1] - h->list_off[sg];
+    const uint32_t size_b = group == 3 ? h->list_off[4 * S + sr + 1] - h->list_off[4 * S + sr] : 0;
+    const uint32_t size = size_a + size_b;
     if (size == 0) {
       continue;
     }
-    const int group = static_cast<int>(sg / S);
-    sa.list = h->order.p + off;
-    sa.list_size = size;
     sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
     ca.base_commit = sa.base_commit;
     reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
+    h->cur_subround = sr;
+    sa.list = h->order.p + h->list_off[sg];
+    sa.list_size = size_a;
     KMP_CUDA(launch_sweep(h, rc.mode, group, sa));
+    if (size_b > 0) {
+      sa.list = h->order.p + h->list_off[4 * S + sr];
+      sa.list_size = size_b;
+      KMP_CUDA(launch_sweep(h, rc.mode, 4, sa));
+    }
     const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
     if (rc.mode == 0) {
       commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
@@ -591,7 +670,7 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   h->kernel_launches = 0;
   h->sweep_launches = 0;
   h->sweep_events_used = 0;
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < 8; ++g) {
     h->group_launches[g] = 0;
   }
   KMP_CUDA(cudaEventRecord(h->ev_begin, h->stream));
@@ -602,14 +681,14 @@ int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   KMP_CUDA(cudaEventRecord(h->ev_end, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   if (stats != nullptr) {
-    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long c[16] = {0};
     KMP_CUDA(cudaMemcpy(c, h->ctr64.p, sizeof(c), cudaMemcpyDeviceToHost));
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < 8; ++g) {
       stats->group_edges[g] = c[g];
-      stats->group_nodes[g] = c[4 + g];
+      stats->group_nodes[g] = c[8 + g];
       stats->group_launches[g] = h->group_launches[g];
       stats->edges_scanned += c[g];
-      stats->nodes_visited += c[4 + g];
+      stats->nodes_visited += c[8 + g];
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
@@ -769,11 +848,16 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_CUDA, "failed to create stream/events");
   }
   {
-    const int smem = kBlockTableSlots * 8;
-    cudaFuncSetAttribute(sweep_block<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sweep_block<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sweep_block<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(sweep_block<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem_g = kGroupTableSlots * kGroupsPerBlock * 8;
+    cudaFuncSetAttribute(sweep_group<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
+    cudaFuncSetAttribute(sweep_group<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
+    cudaFuncSetAttribute(sweep_group<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
+    cudaFuncSetAttribute(sweep_group<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
+    const int smem_c = kChunkTableSlots * 8;
+    cudaFuncSetAttribute(sweep_hub_aggregate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
+    cudaFuncSetAttribute(sweep_hub_aggregate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
+    cudaFuncSetAttribute(sweep_hub_aggregate<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
+    cudaFuncSetAttribute(sweep_hub_aggregate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
   }
   *out = h;
   return KMP_OK;
@@ -825,7 +909,7 @@ static int set_graph_common(kmp_lp_handle *h, uint32_t n, uint32_t m) {
     // vertices in the tail bucket are either isolated or above the degree threshold; count isolated
     // ones exactly only when a post pass needs them (cheap: tail bucket size is an upper bound)
     const uint32_t S = h->lists_S;
-    h->num_isolated = h->list_off[kNumGroups * S + 1] - h->list_off[kNumGroups * S];
+    h->num_isolated = h->list_off[kNumTiers * S + 1] - h->list_off[kNumTiers * S];
   }
   return KMP_OK;
 }
@@ -894,7 +978,7 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   if (n > 0) {
     k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p,
                                                             h->active.p);
@@ -1003,7 +1087,7 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
   if (n > 0) {
     k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
@@ -1071,7 +1155,7 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
       KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
     }
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 16 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
@@ -1080,11 +1164,12 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
   sa.base_fav = sync_base(h->cfg.seed, call_index, iteration, SALT_FAV);
   const uint32_t S = h->lists_S;
-  for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
+  for (uint32_t sg = 0; sg < kNumTiers * S; ++sg) {
     const uint32_t off = h->list_off[sg];
     const uint32_t size = h->list_off[sg + 1] - off;
     sa.list = h->order.p + off;
     sa.list_size = size;
+    h->cur_subround = sg % S;
     KMP_CUDA(launch_sweep(h, mode, static_cast<int>(sg / S), sa));
   }
   KMP_CUDA(cudaMemcpyAsync(target_out, d_target.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1139,12 +1224,12 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out) {
     return fail(KMP_ERR_INVALID, "bad argument");
   }
   KMP_CUDA(cudaSetDevice(h->device));
-  KMP_CUDA(h->ctr64.ensure(16));
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 12, 0, sizeof(unsigned long long), h->stream));
+  KMP_CUDA(h->ctr64.ensure(32));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 24, 0, sizeof(unsigned long long), h->stream));
   k_edge_cut<<<grid_for(static_cast<uint64_t>(h->n) * 32, 256), 256, 0, h->stream>>>(h->n, h->xadj, h->adjncy, h->adjwgt,
-                                                                                      h->label.p, h->ctr64.p + 12);
+                                                                                      h->label.p, h->ctr64.p + 24);
   unsigned long long c = 0;
-  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 12, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 24, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *cut_out = static_cast<int64_t>(c / 2); // metrics.cc:51-52
   return KMP_OK;

@@ -139,14 +139,10 @@ struct SweepArgs {
   uint32_t *__restrict__ mover_count;
   int32_t *__restrict__ incoming;      // clusterer: [n]
   int32_t *__restrict__ hist;          // refiner: [k][16]
-  unsigned long long *__restrict__ counters; // [0] edges scanned, [4] nodes visited (of this degree group)
+  unsigned long long *__restrict__ counters; // [0] edges scanned, [8] nodes visited (of this kernel tier)
   // select_all mode (T0 parity hook): write decisions instead of proposing
   uint32_t *__restrict__ sel_target;
   uint32_t *__restrict__ sel_favored;
-  // hub scratch (global hash tables)
-  uint32_t *__restrict__ hub_keys;
-  int32_t *__restrict__ hub_vals;
-  uint32_t hub_stride; // slots per CTA
 };
 
 // Evaluate one (key, rating) candidate of vertex u. Returns the "best" candidate; fills `fav`.

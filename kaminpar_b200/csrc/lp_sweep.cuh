@@ -3,8 +3,10 @@
 //   group 0 (deg 1..7)    sweep_thread : one thread per vertex, neighbour labels in registers
 //   group 1 (deg 8..31)   sweep_warp   : one warp per vertex, duplicates merged with match.any
 //   group 2 (deg 32..255) sweep_warp_hash : one warp per vertex, per-warp shared-memory hash map
-//   group 3 (deg >= 256)  sweep_block  : one CTA per vertex, CTA-wide shared-memory hash map or a
-//                                        global-memory table for very large neighbourhoods
+//   tier 3 (deg 256..2047) sweep_group : 128 threads per vertex, 4096-slot shared-memory hash map
+//   tier 4 (deg >= 2048)   sweep_hub_aggregate + sweep_hub_select : edge-parallel; 4096-edge chunks
+//                          are aggregated in shared memory and merged into a global table region
+//   (tiers 3 and 4 together are degree group 3 of the schedule)
 //
 // Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
 // rating[label[v]] += w(u,v) over adj(u) (:487-505), clear active[u] (:507-508), select
@@ -39,7 +41,7 @@ __device__ __forceinline__ void block_count_flush(const SweepArgs &a, unsigned l
   }
   if ((threadIdx.x & 31) == 0 && nodes != 0) {
     atomicAdd(&a.counters[0], edges); // counters points at this degree group's slot
-    atomicAdd(&a.counters[4], nodes);
+    atomicAdd(&a.counters[8], nodes);
   }
 }
 
@@ -356,30 +358,42 @@ __global__ void __launch_bounds__(kWarpsPerBlockG2 * 32) sweep_warp_hash(const S
 }
 
 // ================================================================================================
-// group 3: CTA per vertex (deg >= 256): CTA-wide shared hash map, global table for huge hubs
+// tier 3 (256 <= deg < 2048): 128 threads per vertex, 4096-slot shared-memory hash map per group
 // ================================================================================================
-constexpr int kBlockTableSlots = 8192; // 64 KiB of dynamic shared memory
-constexpr int kBlockThreadsG3 = 512;
+constexpr int kGroupThreads = 128;
+constexpr int kGroupsPerBlock = 2;
+constexpr int kGroupTableSlots = 4096;
+constexpr uint32_t kTier4MinDegree = 2048;
 
-template <int MODE, bool EW> __global__ void __launch_bounds__(kBlockThreadsG3) sweep_block(const SweepArgs a) {
+__device__ __forceinline__ void group_barrier(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kGroupThreads) : "memory");
+}
+
+template <int MODE, bool EW>
+__global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(const SweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *s_keys = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *s_vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kBlockTableSlots);
-  __shared__ Cand s_best[kBlockThreadsG3 / 32];
-  __shared__ Cand s_fav[kBlockThreadsG3 / 32];
-  const int tid = threadIdx.x;
+  __shared__ Cand s_best[kGroupsPerBlock][kGroupThreads / 32];
+  __shared__ Cand s_fav[kGroupsPerBlock][kGroupThreads / 32];
+  const int grp = threadIdx.x / kGroupThreads;
+  const int tid = threadIdx.x % kGroupThreads;
   const int lane = tid & 31;
-  const int wib = tid >> 5;
-  for (int s = tid; s < kBlockTableSlots; s += kBlockThreadsG3) {
-    s_keys[s] = kEmpty;
-    s_vals[s] = 0;
+  const int wig = tid >> 5;
+  uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw) + grp * kGroupTableSlots;
+  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kGroupTableSlots * kGroupsPerBlock) +
+                  grp * kGroupTableSlots;
+  for (int s = tid; s < kGroupTableSlots; s += kGroupThreads) {
+    keys[s] = kEmpty;
+    vals[s] = 0;
   }
-  __syncthreads();
+  group_barrier(1 + grp);
   unsigned long long edges = 0, nodes = 0;
-  for (uint32_t i = blockIdx.x; i < a.list_size; i += gridDim.x) {
+  const uint32_t gid = blockIdx.x * kGroupsPerBlock + grp;
+  const uint32_t ngroups = gridDim.x * kGroupsPerBlock;
+  for (uint32_t i = gid; i < a.list_size; i += ngroups) {
     const uint32_t u = a.list[i];
-    if (a.active != nullptr && a.active[u] == 0) {
-      continue; // uniform across the CTA
+    const bool act = a.active == nullptr || a.active[u] != 0; // uniform: written only after barriers
+    if (!act) {
+      continue;
     }
     const uint32_t beg = a.xadj[u];
     uint32_t deg = a.xadj[u + 1] - beg;
@@ -395,42 +409,239 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(kBlockThreadsG3) 
       skip = (own_w - uw) < mn;
     }
     const uint32_t distinct = deg < a.num_labels ? deg : a.num_labels;
-    const bool direct = a.num_labels <= static_cast<uint32_t>(kBlockTableSlots);
+    const bool direct = a.num_labels <= static_cast<uint32_t>(kGroupTableSlots);
     uint32_t cap = direct ? pow2_ceil(a.num_labels) : pow2_ceil(2 * distinct);
     if (cap < 32) {
       cap = 32;
     }
-    uint32_t *keys = s_keys;
-    int32_t *vals = s_vals;
-    if (cap > static_cast<uint32_t>(kBlockTableSlots)) { // huge hub: global table of this CTA
-      keys = a.hub_keys + static_cast<size_t>(blockIdx.x) * a.hub_stride;
-      vals = a.hub_vals + static_cast<size_t>(blockIdx.x) * a.hub_stride;
-      if (cap > a.hub_stride) {
-        cap = a.hub_stride; // hub_stride = pow2_ceil(2 * max degree) >= needed
-      }
-    }
     const uint32_t mask = cap - 1;
     if (!skip) {
-      for (uint32_t e = tid; e < deg; e += kBlockThreadsG3) {
-        const uint32_t v = a.adjncy[beg + e];
-        bool ok = true;
-        if (MODE == 1 && a.communities != nullptr) {
-          ok = a.communities[u] == a.communities[v];
+      for (uint32_t e0 = 0; e0 < deg; e0 += kGroupThreads * 4) {
+        uint32_t k4[4];
+        int32_t w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { // four independent gathers in flight per thread
+          const uint32_t e = e0 + j * kGroupThreads + tid;
+          k4[j] = kEmpty;
+          w4[j] = 0;
+          if (e < deg) {
+            const uint32_t v = a.adjncy[beg + e];
+            bool ok = true;
+            if (MODE == 1 && a.communities != nullptr) {
+              ok = a.communities[u] == a.communities[v];
+            }
+            if (ok) {
+              k4[j] = a.label[v];
+              w4[j] = EW ? a.adjwgt[beg + e] : 1;
+            }
+          }
         }
-        if (ok) {
-          table_add(keys, vals, mask, direct, a.label[v], EW ? a.adjwgt[beg + e] : 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (k4[j] != kEmpty) {
+            table_add(keys, vals, mask, direct, k4[j], w4[j]);
+          }
         }
       }
     }
-    __syncthreads();
+    group_barrier(1 + grp);
     const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
     Cand c = cand_none(), f = cand_none();
-    for (uint32_t s = tid; s < cap; s += kBlockThreadsG3) {
+    for (uint32_t s = tid; s < cap; s += kGroupThreads) {
       const uint32_t k = keys[s];
       if (k != kEmpty) {
         const int32_t r = vals[s];
         keys[s] = kEmpty;
         vals[s] = 0;
+        Cand ff;
+        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
+        if (cand_better<MODE>(cc, c)) {
+          c = cc;
+        }
+        if (MODE == 0 && cand_better<0>(ff, f)) {
+          f = ff;
+        }
+      }
+    }
+    const Cand wb = warp_argmax<MODE>(kFull, c);
+    const Cand wf = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
+    if (lane == 0) {
+      s_best[grp][wig] = wb;
+      s_fav[grp][wig] = wf;
+    }
+    group_barrier(1 + grp);
+    if (tid == 0) {
+      Cand best = cand_none(), fav = cand_none();
+#pragma unroll
+      for (int q = 0; q < kGroupThreads / 32; ++q) {
+        if (cand_better<MODE>(s_best[grp][q], best)) {
+          best = s_best[grp][q];
+        }
+        if (MODE == 0 && cand_better<0>(s_fav[grp][q], fav)) {
+          fav = s_fav[grp][q];
+        }
+      }
+      edges += deg;
+      nodes += 1;
+      if (a.active != nullptr) {
+        a.active[u] = 0;
+      }
+      uint32_t target;
+      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
+        const uint32_t idx = atomicAdd(a.mover_count, 1u);
+        emit_proposal<MODE>(a, idx, u, target, uw);
+      }
+    }
+    group_barrier(1 + grp); // table reset and s_best consumed before the next vertex
+  }
+  block_count_flush(a, edges, nodes);
+}
+
+// ================================================================================================
+// tier 4 (deg >= 2048): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
+// shared-memory hash map and merges the distinct keys into the vertex's global table region.
+// Phase 2: one CTA per vertex scans its region, selects, and clears it.
+// ================================================================================================
+constexpr int kChunkEdges = 4096;
+constexpr int kChunkTableSlots = 8192; // 64 KiB dynamic shared memory
+constexpr int kChunkThreads = 256;
+
+struct HubArgs {
+  const uint32_t *__restrict__ item_entry; // index into the tier-4 list of this sub-round
+  const uint32_t *__restrict__ item_chunk;
+  uint32_t num_items;
+  const uint32_t *__restrict__ table_off;  // per list entry: first slot of its region
+  uint32_t *__restrict__ g_keys;
+  int32_t *__restrict__ g_vals;
+};
+
+__device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_labels) {
+  const uint32_t distinct = full_degree < num_labels ? full_degree : num_labels;
+  const uint32_t cap = pow2_ceil(2 * distinct);
+  return cap < 32 ? 32 : cap;
+}
+
+template <int MODE, bool EW>
+__global__ void __launch_bounds__(kChunkThreads) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
+  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kChunkTableSlots);
+  const int tid = threadIdx.x;
+  for (int s = tid; s < kChunkTableSlots; s += kChunkThreads) {
+    keys[s] = kEmpty;
+    vals[s] = 0;
+  }
+  __syncthreads();
+  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x) {
+    const uint32_t entry = hb.item_entry[it];
+    const uint32_t u = a.list[entry];
+    if (a.active != nullptr && a.active[u] == 0) {
+      continue; // uniform; active[u] is cleared by phase 2 only
+    }
+    const uint32_t beg0 = a.xadj[u];
+    const uint32_t full_deg = a.xadj[u + 1] - beg0;
+    uint32_t deg = full_deg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t cbeg = hb.item_chunk[it] * kChunkEdges;
+    if (cbeg >= deg) {
+      continue;
+    }
+    const uint32_t cend = (cbeg + kChunkEdges < deg) ? cbeg + kChunkEdges : deg;
+    if (MODE == 1) {
+      const uint32_t own = a.label[u];
+      const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+      if ((a.weight[own] - uw) < mn) {
+        continue; // lp_refiner.cc:160-162: no ratings needed
+      }
+    }
+    const uint32_t len = cend - cbeg;
+    const uint32_t ldistinct = len < a.num_labels ? len : a.num_labels;
+    const bool ldirect = a.num_labels <= static_cast<uint32_t>(kChunkTableSlots);
+    uint32_t lcap = ldirect ? pow2_ceil(a.num_labels) : pow2_ceil(2 * ldistinct);
+    if (lcap < 32) {
+      lcap = 32;
+    }
+    const uint32_t lmask = lcap - 1;
+    for (uint32_t e0 = cbeg; e0 < cend; e0 += kChunkThreads * 4) {
+      uint32_t k4[4];
+      int32_t w4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t e = e0 + j * kChunkThreads + tid;
+        k4[j] = kEmpty;
+        w4[j] = 0;
+        if (e < cend) {
+          const uint32_t v = a.adjncy[beg0 + e];
+          bool ok = true;
+          if (MODE == 1 && a.communities != nullptr) {
+            ok = a.communities[u] == a.communities[v];
+          }
+          if (ok) {
+            k4[j] = a.label[v];
+            w4[j] = EW ? a.adjwgt[beg0 + e] : 1;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k4[j] != kEmpty) {
+          table_add(keys, vals, lmask, ldirect, k4[j], w4[j]);
+        }
+      }
+    }
+    __syncthreads();
+    // merge the distinct keys of this chunk into the vertex's global region
+    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+    const bool gdirect = a.num_labels <= gcap;
+    uint32_t *gk = hb.g_keys + hb.table_off[entry];
+    int32_t *gv = hb.g_vals + hb.table_off[entry];
+    for (uint32_t s = tid; s < lcap; s += kChunkThreads) {
+      const uint32_t k = keys[s];
+      if (k != kEmpty) {
+        const int32_t r = vals[s];
+        keys[s] = kEmpty;
+        vals[s] = 0;
+        table_add(gk, gv, gcap - 1, gdirect, k, r);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_select(const SweepArgs a, const HubArgs hb) {
+  __shared__ Cand s_best[kChunkThreads / 32];
+  __shared__ Cand s_fav[kChunkThreads / 32];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int wib = tid >> 5;
+  unsigned long long edges = 0, nodes = 0;
+  for (uint32_t i = blockIdx.x; i < a.list_size; i += gridDim.x) {
+    const uint32_t u = a.list[i];
+    if (a.active != nullptr && a.active[u] == 0) {
+      continue;
+    }
+    const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
+    uint32_t deg = full_deg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t own = a.label[u];
+    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+    const int32_t own_w = a.weight[own];
+    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+    uint32_t *gk = hb.g_keys + hb.table_off[i];
+    int32_t *gv = hb.g_vals + hb.table_off[i];
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand c = cand_none(), f = cand_none();
+    for (uint32_t s = tid; s < gcap; s += kChunkThreads) {
+      const uint32_t k = gk[s];
+      if (k != kEmpty) {
+        const int32_t r = gv[s];
+        gk[s] = kEmpty;
+        gv[s] = 0;
         Cand ff;
         const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
         if (cand_better<MODE>(cc, c)) {
@@ -450,7 +661,8 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(kBlockThreadsG3) 
     __syncthreads();
     if (tid == 0) {
       Cand best = cand_none(), fav = cand_none();
-      for (int q = 0; q < kBlockThreadsG3 / 32; ++q) {
+#pragma unroll
+      for (int q = 0; q < kChunkThreads / 32; ++q) {
         if (cand_better<MODE>(s_best[q], best)) {
           best = s_best[q];
         }
@@ -469,7 +681,7 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(kBlockThreadsG3) 
         emit_proposal<MODE>(a, idx, u, target, uw);
       }
     }
-    __syncthreads(); // table fully reset and s_best consumed before the next vertex
+    __syncthreads();
   }
   block_count_flush(a, edges, nodes);
 }

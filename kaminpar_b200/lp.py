@@ -65,10 +65,10 @@ class KmpStats(C.Structure):
         ("sweep_ms", C.c_float),
         ("sweep_launches", C.c_uint64),
         ("kernel_launches", C.c_uint64),
-        ("group_edges", C.c_uint64 * 4),
-        ("group_nodes", C.c_uint64 * 4),
-        ("group_launches", C.c_uint64 * 4),
-        ("group_sweep_ms", C.c_float * 4),
+        ("group_edges", C.c_uint64 * 8),
+        ("group_nodes", C.c_uint64 * 8),
+        ("group_launches", C.c_uint64 * 8),
+        ("group_sweep_ms", C.c_float * 8),
     ]
 
     def moved_list(self):
