@@ -119,8 +119,9 @@ struct kmp_lp_handle {
   DevBuf<unsigned long long> ctr64; // [0] edges [1] nodes [2] proposals
   // tier 4 (deg >= 2048): per list entry the first slot of its global table region, and the
   // (entry, chunk) work items of phase 1; all per sub-round
-  DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk;
-  std::vector<uint32_t> t4_item_off; // S + 1
+  DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk, t4_sel_entry, t4_sel_piece, t4_sel_begin;
+  std::vector<uint32_t> t4_item_off, t4_sel_off; // S + 1
+  DevBuf<Cand> t4_part_best, t4_part_fav;
   uint64_t t4_max_slots = 0;
   DevBuf<uint32_t> hub_keys;
   DevBuf<int32_t> hub_vals;
@@ -333,8 +334,15 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
       sweep_hub_aggregate<MODE, EW>
           <<<std::min<uint32_t>(hb.num_items, kSMs * 12), kChunkThreads, smem, h->stream>>>(a, hb);
     }
-    sweep_hub_select<MODE><<<std::min<uint32_t>(a.list_size, kSMs * 8), kChunkThreads, 0, h->stream>>>(a, hb);
-    ++h->kernel_launches;
+    hb.sel_entry = h->t4_sel_entry.p + h->t4_sel_off[s_idx];
+    hb.sel_piece = h->t4_sel_piece.p + h->t4_sel_off[s_idx];
+    hb.num_sel_items = h->t4_sel_off[s_idx + 1] - h->t4_sel_off[s_idx];
+    hb.sel_begin = h->t4_sel_begin.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
+    hb.part_best = h->t4_part_best.p;
+    hb.part_fav = h->t4_part_fav.p;
+    sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->stream>>>(a, hb);
+    sweep_hub_final<MODE><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->stream>>>(a, hb);
+    h->kernel_launches += 2;
     break;
   }
   }
@@ -436,7 +444,9 @@ int ensure_lists(kmp_lp_handle *h) {
       DevBuf<uint32_t> d_deg;
       KMP_CUDA(d_deg.ensure(t4_cnt));
       k_gather_degrees<<<grid_for(t4_cnt, 256), 256, 0, h->stream>>>(t4_cnt, h->order.p + t4_begin, h->xadj, d_deg.p);
-      std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), ient, ichk;
+      std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), sbeg(t4_cnt), ient, ichk, sent, spiece;
+      h->t4_sel_off.assign(S + 1, 0);
+      size_t max_sel = 0;
       KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       KMP_CUDA(cudaStreamSynchronize(h->stream));
       d_deg.release();
@@ -458,7 +468,15 @@ int ensure_lists(kmp_lp_handle *h) {
             ient.push_back(i - lo);
             ichk.push_back(c);
           }
+          sbeg[i] = static_cast<uint32_t>(sent.size() - h->t4_sel_off[sr]);
+          const uint32_t pieces = static_cast<uint32_t>((cap + kSelPieceSlots - 1) / kSelPieceSlots);
+          for (uint32_t c = 0; c < pieces; ++c) {
+            sent.push_back(i - lo);
+            spiece.push_back(c);
+          }
         }
+        h->t4_sel_off[sr + 1] = static_cast<uint32_t>(sent.size());
+        max_sel = std::max<size_t>(max_sel, sent.size() - h->t4_sel_off[sr]);
         h->t4_max_slots = std::max(h->t4_max_slots, slots);
         h->t4_item_off[sr + 1] = static_cast<uint32_t>(ient.size());
       }
@@ -468,6 +486,14 @@ int ensure_lists(kmp_lp_handle *h) {
       KMP_CUDA(cudaMemcpyAsync(h->t4_table_off.p, toff.data(), t4_cnt * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(cudaMemcpyAsync(h->t4_item_entry.p, ient.data(), ient.size() * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(cudaMemcpyAsync(h->t4_item_chunk.p, ichk.data(), ichk.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(h->t4_sel_entry.ensure(sent.size()));
+      KMP_CUDA(h->t4_sel_piece.ensure(spiece.size()));
+      KMP_CUDA(h->t4_sel_begin.ensure(t4_cnt));
+      KMP_CUDA(h->t4_part_best.ensure(max_sel));
+      KMP_CUDA(h->t4_part_fav.ensure(max_sel));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_sel_entry.p, sent.data(), sent.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_sel_piece.p, spiece.data(), spiece.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_sel_begin.p, sbeg.data(), t4_cnt * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(cudaStreamSynchronize(h->stream));
     }
   }
@@ -515,7 +541,7 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
     KMP_CUDA(cudaMemsetAsync(h->hist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
     KMP_CUDA(cudaMemsetAsync(h->ohist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
   }
-  // global table regions of tier 4 (kept clean by sweep_hub_select)
+  // global table regions of tier 4 (kept clean by sweep_hub_partial)
   if (h->t4_max_slots > 0 && h->hub_keys.cap < h->t4_max_slots) {
     KMP_CUDA(h->hub_keys.ensure(h->t4_max_slots));
     KMP_CUDA(h->hub_vals.ensure(h->t4_max_slots));

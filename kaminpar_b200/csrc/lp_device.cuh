@@ -146,16 +146,16 @@ struct SweepArgs {
 };
 
 // Evaluate one (key, rating) candidate of vertex u. Returns the "best" candidate; fills `fav`.
+// kw = weight[key] (the caller may have batched the gather)
 template <int MODE>
-__device__ __forceinline__ Cand eval_candidate(const SweepArgs &a, uint32_t u, uint32_t own, int32_t uw,
-                                               int32_t own_w, uint32_t key, int32_t rating, bool store_fav,
-                                               Cand &fav) {
+__device__ __forceinline__ Cand eval_candidate_w(const SweepArgs &a, uint32_t u, uint32_t own, int32_t uw,
+                                                 int32_t own_w, uint32_t key, int32_t rating, int32_t kw,
+                                                 bool store_fav, Cand &fav) {
   Cand c = cand_none();
   fav = cand_none();
   if (rating <= 0) {
     return c;
   }
-  const int32_t kw = a.weight[key];
   if (MODE == 0) {
     bool feasible = (kw + uw <= a.max_cluster_weight) || (key == own);
     if (a.communities != nullptr) {
@@ -186,6 +186,17 @@ __device__ __forceinline__ Cand eval_candidate(const SweepArgs &a, uint32_t u, u
     }
   }
   return c;
+}
+
+template <int MODE>
+__device__ __forceinline__ Cand eval_candidate(const SweepArgs &a, uint32_t u, uint32_t own, int32_t uw,
+                                               int32_t own_w, uint32_t key, int32_t rating, bool store_fav,
+                                               Cand &fav) {
+  if (rating <= 0) {
+    fav = cand_none();
+    return cand_none();
+  }
+  return eval_candidate_w<MODE>(a, u, own, uw, own_w, key, rating, a.weight[key], store_fav, fav);
 }
 
 // Final per-vertex action (one thread): propose a move or store the favored cluster.

@@ -251,6 +251,40 @@ __device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_
   }
 }
 
+// B independent inserts into a global-memory table: the first probe of all B keys is issued before
+// any result is consumed (memory-level parallelism); collisions fall back to sequential probing.
+template <int B>
+__device__ __forceinline__ void table_add_batch(uint32_t *keys, int32_t *vals, uint32_t mask, bool direct,
+                                                const uint32_t (&k)[B], const int32_t (&w)[B]) {
+  uint32_t slot[B], prev[B];
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    slot[j] = direct ? k[j] : (lowbias32(k[j]) & mask);
+    prev[j] = kEmpty;
+    if (k[j] != kEmpty) {
+      prev[j] = atomicCAS(&keys[slot[j]], kEmpty, k[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < B; ++j) {
+    if (k[j] != kEmpty) {
+      if (prev[j] == kEmpty || prev[j] == k[j]) {
+        atomicAdd(&vals[slot[j]], w[j]);
+      } else {
+        uint32_t sl = (slot[j] + 1) & mask;
+        while (true) {
+          const uint32_t pv = atomicCAS(&keys[sl], kEmpty, k[j]);
+          if (pv == kEmpty || pv == k[j]) {
+            atomicAdd(&vals[sl], w[j]);
+            break;
+          }
+          sl = (sl + 1) & mask;
+        }
+      }
+    }
+  }
+}
+
 // ================================================================================================
 // group 2: warp per vertex, per-warp shared-memory hash map (deg <= 256)
 // ================================================================================================
@@ -310,33 +344,69 @@ __global__ void __launch_bounds__(kWarpsPerBlockG2 * 32) sweep_warp_hash(const S
     }
     const uint32_t mask = cap - 1;
     if (!skip) {
-      for (uint32_t e = lane; e < deg; e += 32) {
-        const uint32_t v = a.adjncy[beg + e];
-        bool ok = true;
-        if (MODE == 1 && a.communities != nullptr) {
-          ok = a.communities[u] == a.communities[v];
+      for (uint32_t e0 = 0; e0 < deg; e0 += 32 * 8) {
+        uint32_t kb[8];
+        int32_t wb8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { // up to 8 independent gathers per lane in flight
+          const uint32_t e = e0 + j * 32 + lane;
+          kb[j] = kEmpty;
+          wb8[j] = 0;
+          if (e < deg) {
+            const uint32_t v = a.adjncy[beg + e];
+            bool ok = true;
+            if (MODE == 1 && a.communities != nullptr) {
+              ok = a.communities[u] == a.communities[v];
+            }
+            if (ok) {
+              kb[j] = a.label[v];
+              wb8[j] = EW ? a.adjwgt[beg + e] : 1;
+            }
+          }
         }
-        if (ok) {
-          table_add(keys, vals, mask, direct, a.label[v], EW ? a.adjwgt[beg + e] : 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (kb[j] != kEmpty) {
+            table_add(keys, vals, mask, direct, kb[j], wb8[j]);
+          }
         }
       }
     }
     __syncwarp();
     const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
     Cand c = cand_none(), f = cand_none();
-    for (uint32_t s = lane; s < cap; s += 32) {
-      const uint32_t k = keys[s];
-      if (k != kEmpty) {
-        const int32_t r = vals[s];
-        keys[s] = kEmpty;
-        vals[s] = 0;
-        Cand ff;
-        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
-        if (cand_better<MODE>(cc, c)) {
-          c = cc;
+    for (uint32_t s0 = 0; s0 < cap; s0 += 32 * 8) {
+      uint32_t kb[8];
+      int32_t rb[8], wb8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t s = s0 + j * 32 + lane;
+        kb[j] = kEmpty;
+        rb[j] = 0;
+        if (s < cap) {
+          kb[j] = keys[s];
+          if (kb[j] != kEmpty) {
+            rb[j] = vals[s];
+            keys[s] = kEmpty;
+            vals[s] = 0;
+          }
         }
-        if (MODE == 0 && cand_better<0>(ff, f)) {
-          f = ff;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wb8[j] = kb[j] != kEmpty ? a.weight[kb[j]] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kb[j] != kEmpty) {
+          Cand ff;
+          const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kb[j], rb[j], wb8[j], store_fav, ff);
+          if (cand_better<MODE>(cc, c)) {
+            c = cc;
+          }
+          if (MODE == 0 && cand_better<0>(ff, f)) {
+            f = ff;
+          }
         }
       }
     }
@@ -447,19 +517,38 @@ __global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(co
     group_barrier(1 + grp);
     const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
     Cand c = cand_none(), f = cand_none();
-    for (uint32_t s = tid; s < cap; s += kGroupThreads) {
-      const uint32_t k = keys[s];
-      if (k != kEmpty) {
-        const int32_t r = vals[s];
-        keys[s] = kEmpty;
-        vals[s] = 0;
-        Cand ff;
-        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
-        if (cand_better<MODE>(cc, c)) {
-          c = cc;
+    for (uint32_t s0 = 0; s0 < cap; s0 += kGroupThreads * 8) {
+      uint32_t kb[8];
+      int32_t rb[8], wb8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { // stage 1: shared-memory slots, then the weight gathers in one batch
+        const uint32_t s = s0 + j * kGroupThreads + tid;
+        kb[j] = kEmpty;
+        rb[j] = 0;
+        if (s < cap) {
+          kb[j] = keys[s];
+          if (kb[j] != kEmpty) {
+            rb[j] = vals[s];
+            keys[s] = kEmpty;
+            vals[s] = 0;
+          }
         }
-        if (MODE == 0 && cand_better<0>(ff, f)) {
-          f = ff;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        wb8[j] = kb[j] != kEmpty ? a.weight[kb[j]] : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kb[j] != kEmpty) {
+          Cand ff;
+          const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kb[j], rb[j], wb8[j], store_fav, ff);
+          if (cand_better<MODE>(cc, c)) {
+            c = cc;
+          }
+          if (MODE == 0 && cand_better<0>(ff, f)) {
+            f = ff;
+          }
         }
       }
     }
@@ -502,8 +591,8 @@ __global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(co
 // shared-memory hash map and merges the distinct keys into the vertex's global table region.
 // Phase 2: one CTA per vertex scans its region, selects, and clears it.
 // ================================================================================================
-constexpr int kChunkEdges = 4096;
-constexpr int kChunkTableSlots = 8192; // 64 KiB dynamic shared memory
+constexpr int kChunkEdges = 2048;
+constexpr int kChunkTableSlots = 4096; // 32 KiB dynamic shared memory: 7 CTAs per SM
 constexpr int kChunkThreads = 256;
 
 struct HubArgs {
@@ -513,7 +602,15 @@ struct HubArgs {
   const uint32_t *__restrict__ table_off;  // per list entry: first slot of its region
   uint32_t *__restrict__ g_keys;
   int32_t *__restrict__ g_vals;
+  // phase 2 (partial selection over 8192-slot pieces of the region)
+  const uint32_t *__restrict__ sel_entry;
+  const uint32_t *__restrict__ sel_piece;
+  uint32_t num_sel_items;
+  const uint32_t *__restrict__ sel_begin; // per list entry: its first selection item
+  Cand *__restrict__ part_best;           // per selection item
+  Cand *__restrict__ part_fav;
 };
+constexpr uint32_t kSelPieceSlots = 8192;
 
 __device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_labels) {
   const uint32_t distinct = full_degree < num_labels ? full_degree : num_labels;
@@ -598,57 +695,82 @@ __global__ void __launch_bounds__(kChunkThreads) sweep_hub_aggregate(const Sweep
     const bool gdirect = a.num_labels <= gcap;
     uint32_t *gk = hb.g_keys + hb.table_off[entry];
     int32_t *gv = hb.g_vals + hb.table_off[entry];
-    for (uint32_t s = tid; s < lcap; s += kChunkThreads) {
-      const uint32_t k = keys[s];
-      if (k != kEmpty) {
-        const int32_t r = vals[s];
-        keys[s] = kEmpty;
-        vals[s] = 0;
-        table_add(gk, gv, gcap - 1, gdirect, k, r);
+    for (uint32_t s0 = 0; s0 < lcap; s0 += kChunkThreads * 8) {
+      uint32_t kb[8];
+      int32_t rb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t s = s0 + j * kChunkThreads + tid;
+        kb[j] = kEmpty;
+        rb[j] = 0;
+        if (s < lcap) {
+          kb[j] = keys[s];
+          if (kb[j] != kEmpty) {
+            rb[j] = vals[s];
+            keys[s] = kEmpty;
+            vals[s] = 0;
+          }
+        }
       }
+      table_add_batch<8>(gk, gv, gcap - 1, gdirect, kb, rb);
     }
     __syncthreads();
   }
 }
 
-template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_select(const SweepArgs a, const HubArgs hb) {
+// Phase 2a: one CTA per 8192-slot piece of a hub's region: best candidates of the piece.
+template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_partial(const SweepArgs a, const HubArgs hb) {
   __shared__ Cand s_best[kChunkThreads / 32];
   __shared__ Cand s_fav[kChunkThreads / 32];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int wib = tid >> 5;
-  unsigned long long edges = 0, nodes = 0;
-  for (uint32_t i = blockIdx.x; i < a.list_size; i += gridDim.x) {
-    const uint32_t u = a.list[i];
-    if (a.active != nullptr && a.active[u] == 0) {
-      continue;
-    }
-    const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
-    uint32_t deg = full_deg;
-    if (deg > a.max_num_neighbors) {
-      deg = a.max_num_neighbors;
-    }
-    const uint32_t own = a.label[u];
-    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
-    const int32_t own_w = a.weight[own];
-    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
-    uint32_t *gk = hb.g_keys + hb.table_off[i];
-    int32_t *gv = hb.g_vals + hb.table_off[i];
-    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+  for (uint32_t it = blockIdx.x; it < hb.num_sel_items; it += gridDim.x) {
+    const uint32_t entry = hb.sel_entry[it];
+    const uint32_t u = a.list[entry];
     Cand c = cand_none(), f = cand_none();
-    for (uint32_t s = tid; s < gcap; s += kChunkThreads) {
-      const uint32_t k = gk[s];
-      if (k != kEmpty) {
-        const int32_t r = gv[s];
-        gk[s] = kEmpty;
-        gv[s] = 0;
-        Cand ff;
-        const Cand cc = eval_candidate<MODE>(a, u, own, uw, own_w, k, r, store_fav, ff);
-        if (cand_better<MODE>(cc, c)) {
-          c = cc;
+    const bool act = a.active == nullptr || a.active[u] != 0;
+    if (act) {
+      const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
+      const uint32_t own = a.label[u];
+      const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+      const int32_t own_w = a.weight[own];
+      const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+      const uint32_t lo = hb.sel_piece[it] * kSelPieceSlots;
+      const uint32_t hi = lo + kSelPieceSlots < gcap ? lo + kSelPieceSlots : gcap;
+      uint32_t *gk = hb.g_keys + hb.table_off[entry];
+      int32_t *gv = hb.g_vals + hb.table_off[entry];
+      const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+      constexpr int B = 8; // slots per thread and batch: B independent loads in flight per stage
+      for (uint32_t s0 = lo; s0 < hi; s0 += kChunkThreads * B) {
+        uint32_t kk[B];
+        int32_t rr[B], ww[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          const uint32_t s = s0 + j * kChunkThreads + tid;
+          kk[j] = s < hi ? __ldcg(gk + s) : kEmpty;
         }
-        if (MODE == 0 && cand_better<0>(ff, f)) {
-          f = ff;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          const uint32_t s = s0 + j * kChunkThreads + tid;
+          rr[j] = kk[j] != kEmpty ? __ldcg(gv + s) : 0;
+          ww[j] = kk[j] != kEmpty ? a.weight[kk[j]] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          if (kk[j] != kEmpty) {
+            const uint32_t s = s0 + j * kChunkThreads + tid;
+            gk[s] = kEmpty;
+            gv[s] = 0;
+            Cand ff;
+            const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kk[j], rr[j], ww[j], store_fav, ff);
+            if (cand_better<MODE>(cc, c)) {
+              c = cc;
+            }
+            if (MODE == 0 && cand_better<0>(ff, f)) {
+              f = ff;
+            }
+          }
         }
       }
     }
@@ -670,6 +792,56 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_s
           fav = s_fav[q];
         }
       }
+      hb.part_best[it] = best;
+      hb.part_fav[it] = fav;
+    }
+    __syncthreads();
+  }
+}
+
+// Phase 2b: one warp per hub: reduce its partial results, then propose / store the favored cluster.
+template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const SweepArgs a, const HubArgs hb) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long edges = 0, nodes = 0;
+  for (uint32_t i = warp; i < a.list_size; i += nwarps) {
+    const uint32_t u = a.list[i];
+    if (a.active != nullptr) {
+      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
+      act = __shfl_sync(kFull, act, 0);
+      if (act == 0) {
+        continue;
+      }
+    }
+    const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
+    uint32_t deg = full_deg;
+    if (deg > a.max_num_neighbors) {
+      deg = a.max_num_neighbors;
+    }
+    const uint32_t own = a.label[u];
+    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+    const int32_t own_w = a.weight[own];
+    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+    const uint32_t pieces = (gcap + kSelPieceSlots - 1) / kSelPieceSlots;
+    const uint32_t first = hb.sel_begin[i];
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand c = cand_none(), f = cand_none();
+    for (uint32_t q = lane; q < pieces; q += 32) {
+      const Cand pb = hb.part_best[first + q];
+      if (cand_better<MODE>(pb, c)) {
+        c = pb;
+      }
+      if (MODE == 0) {
+        const Cand pf = hb.part_fav[first + q];
+        if (cand_better<0>(pf, f)) {
+          f = pf;
+        }
+      }
+    }
+    const Cand best = warp_argmax<MODE>(kFull, c);
+    const Cand fav = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
+    if (lane == 0) {
       edges += deg;
       nodes += 1;
       if (a.active != nullptr) {
@@ -681,7 +853,6 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_s
         emit_proposal<MODE>(a, idx, u, target, uw);
       }
     }
-    __syncthreads();
   }
   block_count_flush(a, edges, nodes);
 }
