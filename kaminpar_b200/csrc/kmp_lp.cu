@@ -123,8 +123,7 @@ struct kmp_lp_handle {
   std::vector<uint32_t> t4_item_off, t4_sel_off; // S + 1
   DevBuf<Cand> t4_part_best, t4_part_fav;
   uint64_t t4_max_slots = 0;
-  DevBuf<uint32_t> hub_keys;
-  DevBuf<int32_t> hub_vals;
+  DevBuf<unsigned long long> hub_tab; // packed (key << 32 | rating) entries, kEmpty64 when unused
   uint32_t mover_cap = 0;
   uint32_t cur_subround = 0;
   DevBuf<uint8_t> sort_keys_in, sort_keys_out;
@@ -181,6 +180,12 @@ __global__ void k_init_cluster(uint32_t n, const int32_t *vwgt, uint32_t *label,
     favored[u] = u;
     weight[u] = vwgt != nullptr ? vwgt[u] : 1;
     active[u] = 1;
+  }
+}
+__global__ void k_fill_u64(uint64_t n, unsigned long long *p, unsigned long long v) {
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    p[i] = v;
   }
 }
 __global__ void k_fill_u8(uint32_t n, uint8_t *p, uint8_t v) {
@@ -327,12 +332,9 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     hb.item_chunk = h->t4_item_chunk.p + h->t4_item_off[s_idx];
     hb.num_items = h->t4_item_off[s_idx + 1] - h->t4_item_off[s_idx];
     hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
-    hb.g_keys = h->hub_keys.p;
-    hb.g_vals = h->hub_vals.p;
-    const size_t smem = static_cast<size_t>(kChunkTableSlots) * 8;
+    hb.g_tab = h->hub_tab.p;
     if (hb.num_items > 0) {
-      sweep_hub_aggregate<MODE, EW>
-          <<<std::min<uint32_t>(hb.num_items, kSMs * 12), kChunkThreads, smem, h->stream>>>(a, hb);
+      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 24), kChunkThreads, 0, h->stream>>>(a, hb);
     }
     hb.sel_entry = h->t4_sel_entry.p + h->t4_sel_off[s_idx];
     hb.sel_piece = h->t4_sel_piece.p + h->t4_sel_off[s_idx];
@@ -542,11 +544,10 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
     KMP_CUDA(cudaMemsetAsync(h->ohist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
   }
   // global table regions of tier 4 (kept clean by sweep_hub_partial)
-  if (h->t4_max_slots > 0 && h->hub_keys.cap < h->t4_max_slots) {
-    KMP_CUDA(h->hub_keys.ensure(h->t4_max_slots));
-    KMP_CUDA(h->hub_vals.ensure(h->t4_max_slots));
-    KMP_CUDA(cudaMemsetAsync(h->hub_keys.p, 0xFF, h->t4_max_slots * sizeof(uint32_t), h->stream));
-    KMP_CUDA(cudaMemsetAsync(h->hub_vals.p, 0, h->t4_max_slots * sizeof(int32_t), h->stream));
+  if (h->t4_max_slots > 0 && h->hub_tab.cap < h->t4_max_slots) {
+    KMP_CUDA(h->hub_tab.ensure(h->t4_max_slots));
+    k_fill_u64<<<grid_for(h->t4_max_slots, 256), 256, 0, h->stream>>>(h->t4_max_slots, h->hub_tab.p, kEmpty64);
+    KMP_CUDA(cudaGetLastError());
   }
   (void)num_labels;
   return KMP_OK;
@@ -673,7 +674,12 @@ int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *m
       commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
       h->kernel_launches += 2;
     }
-    commit_activate<<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca);
+    switch (group) {
+    case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+    case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+    case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+    default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+    }
     h->kernel_launches += 1;
     KMP_CUDA(cudaGetLastError());
   }
@@ -1236,8 +1242,7 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ojmin.release();
   h->ctr32.release();
   h->ctr64.release();
-  h->hub_keys.release();
-  h->hub_vals.release();
+  h->hub_tab.release();
   h->cub_tmp.release();
   h->pairs_a.release();
   h->pairs_b.release();

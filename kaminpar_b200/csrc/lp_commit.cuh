@@ -234,20 +234,21 @@ template <int MODE> __global__ void commit_apply(const CommitArgs a) {
 }
 
 // ---- activate neighbours of moved vertices (label_propagation.h:848-870) ----------------------
-// one warp per accepted proposal
-__global__ void commit_activate(const CommitArgs a) {
+// LANES threads cooperate on one accepted proposal (LANES = 4, 8, 32 or the whole 256-thread CTA,
+// chosen by the degree group of the sub-round).
+template <int LANES> __global__ void __launch_bounds__(256) commit_activate(const CommitArgs a) {
   const uint32_t cnt = *a.mover_count;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = warp; i < cnt; i += nwarps) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sub = tid % LANES;
+  const uint32_t nteams = (gridDim.x * blockDim.x) / LANES;
+  for (uint32_t i = tid / LANES; i < cnt; i += nteams) {
     if (a.acc[i] != 1) {
       continue;
     }
     const uint32_t u = a.mv_u[i];
     const uint32_t beg = a.xadj[u];
     const uint32_t end = a.xadj[u + 1];
-    for (uint32_t e = beg + lane; e < end; e += 32) {
+    for (uint32_t e = beg + sub; e < end; e += LANES) {
       a.active[a.adjncy[e]] = 1;
     }
   }

@@ -251,31 +251,41 @@ __device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_
   }
 }
 
-// B independent inserts into a global-memory table: the first probe of all B keys is issued before
-// any result is consumed (memory-level parallelism); collisions fall back to sequential probing.
+// Global hub tables hold packed 64-bit entries (key << 32 | rating); empty = 0xFFFFFFFF00000000.
+// The first insertion of a key is ONE atomicCAS that also deposits the rating; later partial
+// ratings are one 64-bit atomicAdd on the same entry (ratings are non-negative int32 sums).
+constexpr unsigned long long kEmpty64 = 0xFFFFFFFF00000000ull;
+
+// B independent inserts: the first probe of all B keys is issued before any result is consumed.
 template <int B>
-__device__ __forceinline__ void table_add_batch(uint32_t *keys, int32_t *vals, uint32_t mask, bool direct,
-                                                const uint32_t (&k)[B], const int32_t (&w)[B]) {
-  uint32_t slot[B], prev[B];
+__device__ __forceinline__ void table64_add_batch(unsigned long long *tab, uint32_t mask, bool direct,
+                                                  const uint32_t (&k)[B], const int32_t (&w)[B]) {
+  uint32_t slot[B];
+  unsigned long long prev[B];
 #pragma unroll
   for (int j = 0; j < B; ++j) {
     slot[j] = direct ? k[j] : (lowbias32(k[j]) & mask);
-    prev[j] = kEmpty;
+    prev[j] = kEmpty64;
     if (k[j] != kEmpty) {
-      prev[j] = atomicCAS(&keys[slot[j]], kEmpty, k[j]);
+      prev[j] = atomicCAS(&tab[slot[j]], kEmpty64,
+                          (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]));
     }
   }
 #pragma unroll
   for (int j = 0; j < B; ++j) {
-    if (k[j] != kEmpty) {
-      if (prev[j] == kEmpty || prev[j] == k[j]) {
-        atomicAdd(&vals[slot[j]], w[j]);
+    if (k[j] != kEmpty && prev[j] != kEmpty64) {
+      if (static_cast<uint32_t>(prev[j] >> 32) == k[j]) {
+        atomicAdd(&tab[slot[j]], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
       } else {
         uint32_t sl = (slot[j] + 1) & mask;
         while (true) {
-          const uint32_t pv = atomicCAS(&keys[sl], kEmpty, k[j]);
-          if (pv == kEmpty || pv == k[j]) {
-            atomicAdd(&vals[sl], w[j]);
+          const unsigned long long pv =
+              atomicCAS(&tab[sl], kEmpty64, (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]));
+          if (pv == kEmpty64) {
+            break;
+          }
+          if (static_cast<uint32_t>(pv >> 32) == k[j]) {
+            atomicAdd(&tab[sl], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
             break;
           }
           sl = (sl + 1) & mask;
@@ -600,8 +610,7 @@ struct HubArgs {
   const uint32_t *__restrict__ item_chunk;
   uint32_t num_items;
   const uint32_t *__restrict__ table_off;  // per list entry: first slot of its region
-  uint32_t *__restrict__ g_keys;
-  int32_t *__restrict__ g_vals;
+  unsigned long long *__restrict__ g_tab; // packed entries
   // phase 2 (partial selection over 8192-slot pieces of the region)
   const uint32_t *__restrict__ sel_entry;
   const uint32_t *__restrict__ sel_piece;
@@ -619,21 +628,18 @@ __device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_l
 }
 
 template <int MODE, bool EW>
-__global__ void __launch_bounds__(kChunkThreads) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kChunkTableSlots);
-  const int tid = threadIdx.x;
-  for (int s = tid; s < kChunkTableSlots; s += kChunkThreads) {
-    keys[s] = kEmpty;
-    vals[s] = 0;
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb) {
+  // No shared-memory table: the 32 neighbour labels a warp loads together are de-duplicated with
+  // match.any (later LP rounds: most neighbours of a hub share a few labels), the leader of each
+  // group merges the group's rating into the vertex's global region with one 64-bit atomic.
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  constexpr int kWarps = kChunkThreads / 32;
   for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x) {
     const uint32_t entry = hb.item_entry[it];
     const uint32_t u = a.list[entry];
     if (a.active != nullptr && a.active[u] == 0) {
-      continue; // uniform; active[u] is cleared by phase 2 only
+      continue; // active[u] is cleared by phase 2b only
     }
     const uint32_t beg0 = a.xadj[u];
     const uint32_t full_deg = a.xadj[u + 1] - beg0;
@@ -654,20 +660,16 @@ __global__ void __launch_bounds__(kChunkThreads) sweep_hub_aggregate(const Sweep
         continue; // lp_refiner.cc:160-162: no ratings needed
       }
     }
-    const uint32_t len = cend - cbeg;
-    const uint32_t ldistinct = len < a.num_labels ? len : a.num_labels;
-    const bool ldirect = a.num_labels <= static_cast<uint32_t>(kChunkTableSlots);
-    uint32_t lcap = ldirect ? pow2_ceil(a.num_labels) : pow2_ceil(2 * ldistinct);
-    if (lcap < 32) {
-      lcap = 32;
-    }
-    const uint32_t lmask = lcap - 1;
-    for (uint32_t e0 = cbeg; e0 < cend; e0 += kChunkThreads * 4) {
+    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+    const bool gdirect = a.num_labels <= gcap;
+    unsigned long long *gt = hb.g_tab + hb.table_off[entry];
+    // each warp takes batches of 4 x 32 consecutive edges
+    for (uint32_t e0 = cbeg + wib * 128; e0 < cend; e0 += kWarps * 128) {
       uint32_t k4[4];
       int32_t w4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t e = e0 + j * kChunkThreads + tid;
+      for (int j = 0; j < 4; ++j) { // 4 independent gathers per lane in flight
+        const uint32_t e = e0 + j * 32 + lane;
         k4[j] = kEmpty;
         w4[j] = 0;
         if (e < cend) {
@@ -684,37 +686,26 @@ __global__ void __launch_bounds__(kChunkThreads) sweep_hub_aggregate(const Sweep
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (k4[j] != kEmpty) {
-          table_add(keys, vals, lmask, ldirect, k4[j], w4[j]);
-        }
-      }
-    }
-    __syncthreads();
-    // merge the distinct keys of this chunk into the vertex's global region
-    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
-    const bool gdirect = a.num_labels <= gcap;
-    uint32_t *gk = hb.g_keys + hb.table_off[entry];
-    int32_t *gv = hb.g_vals + hb.table_off[entry];
-    for (uint32_t s0 = 0; s0 < lcap; s0 += kChunkThreads * 8) {
-      uint32_t kb[8];
-      int32_t rb[8];
+        const unsigned peers = __match_any_sync(kFull, k4[j]);
+        int32_t r;
+        if (EW) {
+          r = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t s = s0 + j * kChunkThreads + tid;
-        kb[j] = kEmpty;
-        rb[j] = 0;
-        if (s < lcap) {
-          kb[j] = keys[s];
-          if (kb[j] != kEmpty) {
-            rb[j] = vals[s];
-            keys[s] = kEmpty;
-            vals[s] = 0;
+          for (int q = 0; q < 32; ++q) {
+            const int32_t wq = __shfl_sync(kFull, w4[j], q);
+            r += ((peers >> q) & 1u) ? wq : 0;
           }
+        } else {
+          r = __popc(peers);
         }
+        const bool leader = lane == __ffs(peers) - 1;
+        if (!leader) {
+          k4[j] = kEmpty;
+        }
+        w4[j] = r;
       }
-      table_add_batch<8>(gk, gv, gcap - 1, gdirect, kb, rb);
+      table64_add_batch<4>(gt, gcap - 1, gdirect, k4, w4);
     }
-    __syncthreads();
   }
 }
 
@@ -738,8 +729,7 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_p
       const uint32_t gcap = hub_cap(full_deg, a.num_labels);
       const uint32_t lo = hb.sel_piece[it] * kSelPieceSlots;
       const uint32_t hi = lo + kSelPieceSlots < gcap ? lo + kSelPieceSlots : gcap;
-      uint32_t *gk = hb.g_keys + hb.table_off[entry];
-      int32_t *gv = hb.g_vals + hb.table_off[entry];
+      unsigned long long *gt = hb.g_tab + hb.table_off[entry];
       const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
       constexpr int B = 8; // slots per thread and batch: B independent loads in flight per stage
       for (uint32_t s0 = lo; s0 < hi; s0 += kChunkThreads * B) {
@@ -748,20 +738,18 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_p
 #pragma unroll
         for (int j = 0; j < B; ++j) {
           const uint32_t s = s0 + j * kChunkThreads + tid;
-          kk[j] = s < hi ? __ldcg(gk + s) : kEmpty;
+          const unsigned long long e = s < hi ? __ldcg(gt + s) : kEmpty64;
+          kk[j] = static_cast<uint32_t>(e >> 32);
+          rr[j] = static_cast<int32_t>(static_cast<uint32_t>(e));
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          const uint32_t s = s0 + j * kChunkThreads + tid;
-          rr[j] = kk[j] != kEmpty ? __ldcg(gv + s) : 0;
           ww[j] = kk[j] != kEmpty ? a.weight[kk[j]] : 0;
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
           if (kk[j] != kEmpty) {
-            const uint32_t s = s0 + j * kChunkThreads + tid;
-            gk[s] = kEmpty;
-            gv[s] = 0;
+            gt[s0 + j * kChunkThreads + tid] = kEmpty64;
             Cand ff;
             const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kk[j], rr[j], ww[j], store_fav, ff);
             if (cand_better<MODE>(cc, c)) {
