@@ -154,6 +154,31 @@ int kmp_lp_set_timing(kmp_lp_handle *h, int enabled);
 /* Metrics on the device (metrics.cc:36-53): edge cut of the labels currently on the device. */
 int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out);
 
+/* ---- Stepping API: one LP sub-round at a time (sharded multi-GPU driver) ----------------------
+ * One process per GPU; every rank holds a replica of the graph and of the label / weight state,
+ * the vertex frontier (work lists) is sharded. Per sub-round: kmp_lp_step_sweep on the rank's share
+ * -> all-gather of the packed proposal buffers (NCCL) -> kmp_lp_step_commit on every rank (the
+ * commit rule is order-independent, so all replicas stay bit-identical). This is the role of the
+ * reference's distributed twin (kaminpar-dist/refinement/lp/lp_refiner.cc:119-222: local
+ * perform_iteration per chunk, then label exchange) with NCCL instead of MPI. */
+int kmp_lp_set_shard(kmp_lp_handle *h, uint32_t rank, uint32_t world);
+int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream); /* run on the caller's stream (NCCL ordering) */
+uint32_t kmp_lp_num_subrounds(kmp_lp_handle *h);
+/* cap: proposals one rank can emit in sub-round sg (buffer = 4 + 2*cap words); size: vertices in it */
+int kmp_lp_subround_cap(kmp_lp_handle *h, uint32_t sg, uint32_t *cap_out, uint32_t *size_out);
+int kmp_lp_step_begin_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, const uint32_t *communities);
+int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights,
+                             const int32_t *min_block_weights, const uint32_t *communities,
+                             const uint32_t *partition);
+int kmp_lp_step_begin_iteration(kmp_lp_handle *h);
+int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send);
+int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void *d_gathered);
+int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved);
+int kmp_lp_step_favored_export(kmp_lp_handle *h, void *d_buf);
+int kmp_lp_step_favored_import(kmp_lp_handle *h, const void *d_buf);
+int kmp_lp_step_finish(kmp_lp_handle *h, uint32_t *labels_out, int32_t *block_weights_out,
+                       kmp_lp_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,7 +79,8 @@ template <typename T> struct DevBuf {
 struct kmp_lp_handle {
   kmp_lp_config cfg{};
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // stream all work is issued on
+  cudaStream_t owned_stream = nullptr; // the stream this handle created (destroyed with it)
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
@@ -134,6 +135,13 @@ struct kmp_lp_handle {
 
   uint32_t call_counter = 0;
   uint64_t kernel_launches = 0, sweep_launches = 0;
+  // frontier sharding (one process per GPU): this rank sweeps slice `rank` of `world` of every list
+  uint32_t rank = 0, world = 1;
+  // stepping API state
+  int step_mode = -1;
+  uint32_t step_labels = 0;
+  int32_t step_mcw = 0;
+  bool step_has_min = false, step_has_comm = false;
 };
 
 namespace {
@@ -295,6 +303,58 @@ __global__ void k_match_two_hop(uint32_t cnt, const unsigned long long *sorted, 
   }
 }
 
+// ---- exchange helpers of the sharded (multi-GPU) path -------------------------------------------
+// pack this rank's proposals: buf = [count, pad, pad, pad, u[cap], t[cap]]
+__global__ void k_pack_movers(const uint32_t *mv_u, const uint32_t *mv_t, const uint32_t *count, uint32_t cap,
+                              uint32_t *buf) {
+  const uint32_t cnt = *count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    buf[0] = cnt;
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    buf[4 + i] = mv_u[i];
+    buf[4 + cap + i] = mv_t[i];
+  }
+}
+// concatenate the proposals of all ranks (rank order) into mv_u / mv_t
+__global__ void k_unpack_movers(const uint32_t *gathered, uint32_t world, uint32_t cap, uint32_t *mv_u, uint32_t *mv_t,
+                                uint32_t *count) {
+  const uint32_t stride = 4 + 2 * cap;
+  uint32_t total = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    const uint32_t cnt = gathered[static_cast<size_t>(r) * stride];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+      mv_u[total + i] = gathered[static_cast<size_t>(r) * stride + 4 + i];
+      mv_t[total + i] = gathered[static_cast<size_t>(r) * stride + 4 + cap + i];
+    }
+    total += cnt;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *count = total;
+  }
+}
+// incoming[] / hist[] over the gathered proposals (the sweep kernels skip it when world > 1)
+template <int MODE>
+__global__ void k_accumulate_movers(const uint32_t *mv_u, const uint32_t *mv_t, const uint32_t *count,
+                                    const int32_t *vwgt, uint32_t base_commit, int32_t *incoming, int32_t *hist) {
+  const uint32_t cnt = *count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t u = mv_u[i];
+    const int32_t w = vwgt != nullptr ? vwgt[u] : 1;
+    if (MODE == 0) {
+      atomicAdd(&incoming[mv_t[i]], w);
+    } else {
+      atomicAdd(&hist[mv_t[i] * kLadderLevels + ladder_level(bijective32(u, base_commit))], w);
+    }
+  }
+}
+// favored fix-up across ranks: only the owner of u ever writes favored[u] (initially u)
+__global__ void k_xor_iota(uint32_t n, const uint32_t *in, uint32_t *out) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    out[u] = in[u] ^ u;
+  }
+}
+
 // ---- launch helpers -----------------------------------------------------------------------------
 inline uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t max_blocks = kSMs * 16) {
   const uint64_t b = (threads_needed + block - 1) / block;
@@ -333,6 +393,8 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     hb.num_items = h->t4_item_off[s_idx + 1] - h->t4_item_off[s_idx];
     hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
     hb.g_tab = h->hub_tab.p;
+    hb.rank = h->rank;
+    hb.world = h->world;
     if (hb.num_items > 0) {
       sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 24), kChunkThreads, 0, h->stream>>>(a, hb);
     }
@@ -619,69 +681,109 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
 }
 
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
-int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
+struct SubRound {
+  int group;
+  uint32_t sr, size_a, size_b; // full list sizes (tiers <= 3; tier 4)
+  uint32_t lo_a, hi_a;         // this rank's slice of list a
+};
+
+SubRound subround_of_sg(const kmp_lp_handle *h, uint32_t sg) {
+  const uint32_t S = h->lists_S;
+  SubRound q{};
+  q.group = static_cast<int>(sg / S);
+  q.sr = sg % S;
+  q.size_a = h->list_off[sg + 1] - h->list_off[sg];
+  q.size_b = q.group == 3 ? h->list_off[4 * S + q.sr + 1] - h->list_off[4 * S + q.sr] : 0;
+  q.lo_a = static_cast<uint32_t>(static_cast<uint64_t>(q.size_a) * h->rank / h->world);
+  q.hi_a = static_cast<uint32_t>(static_cast<uint64_t>(q.size_a) * (h->rank + 1) / h->world);
+  return q;
+}
+
+// capacity of one rank's proposal buffer for sub-round sg (identical on every rank)
+uint32_t subround_cap(const kmp_lp_handle *h, const SubRound &q) {
+  return (q.size_a + h->world - 1) / h->world + (q.size_b + h->world - 1) / h->world + 1;
+}
+
+// sweep kernels of one sub-round over this rank's share of the lists
+int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
   const uint32_t S = h->lists_S;
   SweepArgs sa = make_sweep_args(h, rc);
-  CommitArgs ca = make_commit_args(h, rc);
   sa.base_tie = sync_base(h->cfg.seed, h->call_counter, iter, SALT_TIE);
   sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // mover, moved, proposals
+  sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  sa.accumulate = h->world == 1;
+  reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
+  h->cur_subround = q.sr;
+  sa.list = h->order.p + h->list_off[sg] + q.lo_a;
+  sa.list_size = q.hi_a - q.lo_a;
+  KMP_CUDA(launch_sweep(h, rc.mode, q.group, sa));
+  if (q.size_b > 0) {
+    sa.list = h->order.p + h->list_off[4 * S + q.sr];
+    sa.list_size = q.size_b;
+    KMP_CUDA(launch_sweep(h, rc.mode, 4, sa));
+  }
+  return KMP_OK;
+}
+
+// commit kernels of one sub-round over the proposals in mv_u / mv_t (count in ctr32[0])
+int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
+  CommitArgs ca = make_commit_args(h, rc);
+  ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  const uint32_t size = q.size_a + q.size_b;
   const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
+  const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
+  if (rc.mode == 0) {
+    commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
+    commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
+    commit_apply<0><<<cgrid, 256, 0, h->stream>>>(ca);
+    h->kernel_launches += 4;
+  } else {
+    const uint32_t kgrid = grid_for(rc.num_labels, 128);
+    commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p);
+    commit_refine_prepare<<<kgrid, 128, 0, h->stream>>>(ca);
+    for (uint32_t p = 0; p < passes; ++p) {
+      commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
+      commit_refine_decide<<<cgrid, 256, 0, h->stream>>>(ca);
+    }
+    h->kernel_launches += 3 + 2 * passes;
+    if (rc.has_min) {
+      commit_refine_ohist<<<cgrid, 256, 0, h->stream>>>(ca);
+      commit_refine_ojmin<<<kgrid, 128, 0, h->stream>>>(ca);
+      commit_refine_othin<<<cgrid, 256, 0, h->stream>>>(ca);
+      h->kernel_launches += 3;
+    }
+    commit_apply<1><<<cgrid, 256, 0, h->stream>>>(ca);
+    commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
+    h->kernel_launches += 2;
+  }
+  switch (q.group) {
+  case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  }
+  h->kernel_launches += 1;
+  KMP_CUDA(cudaGetLastError());
+  return KMP_OK;
+}
+
+// One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
+int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
+  const uint32_t S = h->lists_S;
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // mover, moved, proposals
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
-    const int group = static_cast<int>(sg / S);
-    const uint32_t sr = sg % S;
-    // degree group 3 of the schedule = kernel tiers 3 and 4
-    const uint32_t size_a = h->list_off[sg + 1] - h->list_off[sg];
-    const uint32_t size_b = group == 3 ? h->list_off[4 * S + sr + 1] - h->list_off[4 * S + sr] : 0;
-    const uint32_t size = size_a + size_b;
-    if (size == 0) {
+    const SubRound q = subround_of_sg(h, sg);
+    if (q.size_a + q.size_b == 0) {
       continue;
     }
-    sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-    ca.base_commit = sa.base_commit;
-    reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
-    h->cur_subround = sr;
-    sa.list = h->order.p + h->list_off[sg];
-    sa.list_size = size_a;
-    KMP_CUDA(launch_sweep(h, rc.mode, group, sa));
-    if (size_b > 0) {
-      sa.list = h->order.p + h->list_off[4 * S + sr];
-      sa.list_size = size_b;
-      KMP_CUDA(launch_sweep(h, rc.mode, 4, sa));
+    int rc2 = sweep_subround(h, rc, iter, sg, q);
+    if (rc2 != KMP_OK) {
+      return rc2;
     }
-    const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
-    if (rc.mode == 0) {
-      commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
-      commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
-      commit_apply<0><<<cgrid, 256, 0, h->stream>>>(ca);
-      h->kernel_launches += 4;
-    } else {
-      const uint32_t kgrid = grid_for(rc.num_labels, 128);
-      commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p);
-      commit_refine_prepare<<<kgrid, 128, 0, h->stream>>>(ca);
-      for (uint32_t p = 0; p < passes; ++p) {
-        commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
-        commit_refine_decide<<<cgrid, 256, 0, h->stream>>>(ca);
-      }
-      h->kernel_launches += 3 + 2 * passes;
-      if (rc.has_min) {
-        commit_refine_ohist<<<cgrid, 256, 0, h->stream>>>(ca);
-        commit_refine_ojmin<<<kgrid, 128, 0, h->stream>>>(ca);
-        commit_refine_othin<<<cgrid, 256, 0, h->stream>>>(ca);
-        h->kernel_launches += 3;
-      }
-      commit_apply<1><<<cgrid, 256, 0, h->stream>>>(ca);
-      commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
-      h->kernel_launches += 2;
+    rc2 = commit_subround(h, rc, iter, sg, q);
+    if (rc2 != KMP_OK) {
+      return rc2;
     }
-    switch (group) {
-    case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-    case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-    case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-    default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-    }
-    h->kernel_launches += 1;
-    KMP_CUDA(cudaGetLastError());
   }
   uint32_t host[2] = {0, 0};
   KMP_CUDA(cudaMemcpyAsync(host, h->ctr32.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -874,11 +976,12 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     cudaGetDevice(&dev);
   }
   h->device = dev;
-  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev_begin) != cudaSuccess || cudaEventCreate(&h->ev_end) != cudaSuccess) {
     delete h;
     return fail(KMP_ERR_CUDA, "failed to create stream/events");
   }
+  h->stream = h->owned_stream;
   {
     const int smem_g = kGroupTableSlots * kGroupsPerBlock * 8;
     cudaFuncSetAttribute(sweep_group<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
@@ -913,7 +1016,7 @@ int kmp_lp_destroy(kmp_lp_handle *h) {
   }
   cudaEventDestroy(h->ev_begin);
   cudaEventDestroy(h->ev_end);
-  cudaStreamDestroy(h->stream);
+  cudaStreamDestroy(h->owned_stream);
   delete h;
   return KMP_OK;
 }
@@ -1264,6 +1367,244 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out) {
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *cut_out = static_cast<int64_t>(c / 2); // metrics.cc:51-52
   return KMP_OK;
+}
+
+
+// ================================================================================================
+// Stepping API: one LP sub-round at a time, for the sharded multi-GPU driver (kaminpar_b200/dist.py).
+// Every rank owns a full replica of the graph and of the label / weight / active state; the vertex
+// frontier (the work lists) is sharded across ranks. Per sub-round each rank sweeps its share,
+// the proposals are all-gathered, and every rank runs the same deterministic commit.
+// ================================================================================================
+int kmp_lp_set_shard(kmp_lp_handle *h, uint32_t rank, uint32_t world) {
+  if (h == nullptr || world == 0 || rank >= world) {
+    return fail(KMP_ERR_INVALID, "bad rank/world");
+  }
+  h->rank = rank;
+  h->world = world;
+  return KMP_OK;
+}
+
+int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream) {
+  if (h == nullptr) {
+    return fail(KMP_ERR_INVALID, "null handle");
+  }
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : h->owned_stream;
+  return KMP_OK;
+}
+
+uint32_t kmp_lp_num_subrounds(kmp_lp_handle *h) {
+  return h != nullptr && h->lists_valid ? kNumGroups * h->lists_S : 0;
+}
+
+int kmp_lp_subround_cap(kmp_lp_handle *h, uint32_t sg, uint32_t *cap_out, uint32_t *size_out) {
+  if (h == nullptr || !h->lists_valid || sg >= kNumGroups * h->lists_S) {
+    return fail(KMP_ERR_INVALID, "bad sub-round");
+  }
+  const SubRound q = subround_of_sg(h, sg);
+  if (cap_out != nullptr) {
+    *cap_out = subround_cap(h, q);
+  }
+  if (size_out != nullptr) {
+    *size_out = q.size_a + q.size_b;
+  }
+  return KMP_OK;
+}
+
+int kmp_lp_step_begin_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, const uint32_t *communities) {
+  int rc = begin_call(h, nullptr);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  const uint32_t n = h->n;
+  rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(h->label.ensure(n));
+  KMP_CUDA(h->favored.ensure(n));
+  KMP_CUDA(h->weight.ensure(n));
+  rc = ensure_scratch(h, 0, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  rc = upload_optional_u32(h, h->communities, communities, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  if (n > 0) {
+    k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p, h->active.p);
+  }
+  h->step_mode = 0;
+  h->step_labels = n;
+  h->step_mcw = max_cluster_weight;
+  h->step_has_min = false;
+  h->step_has_comm = communities != nullptr;
+  return KMP_OK;
+}
+
+int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights,
+                             const int32_t *min_block_weights, const uint32_t *communities, const uint32_t *partition) {
+  if (max_block_weights == nullptr || partition == nullptr || k == 0) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  int rc = begin_call(h, nullptr);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  const uint32_t n = h->n;
+  rc = ensure_lists(h);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(h->label.ensure(n));
+  KMP_CUDA(h->weight.ensure(k));
+  KMP_CUDA(h->maxw.ensure(k));
+  rc = ensure_scratch(h, 1, k);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaMemcpyAsync(h->label.p, partition, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(h->maxw.p, max_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (min_block_weights != nullptr) {
+    KMP_CUDA(h->minw.ensure(k));
+    KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = upload_optional_u32(h, h->communities, communities, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
+  if (n > 0) {
+    k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
+    k_fill_u8<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->active.p, 1);
+  }
+  h->step_mode = 1;
+  h->step_labels = k;
+  h->step_mcw = 0;
+  h->step_has_min = min_block_weights != nullptr;
+  h->step_has_comm = communities != nullptr;
+  return KMP_OK;
+}
+
+int kmp_lp_step_begin_iteration(kmp_lp_handle *h) {
+  if (h == nullptr || h->step_mode < 0) {
+    return fail(KMP_ERR_INVALID, "step_begin_* not called");
+  }
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream));
+  return KMP_OK;
+}
+
+// Sweep this rank's share of sub-round sg and pack its proposals into d_send (device memory,
+// 4 + 2 * cap words: [count, -, -, -, u[cap], t[cap]]).
+int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send) {
+  if (h == nullptr || h->step_mode < 0 || d_send == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  const RunCtx rc{h->step_mode, h->step_labels, h->step_mcw, h->step_has_min, h->step_has_comm};
+  const SubRound q = subround_of_sg(h, sg);
+  int r = sweep_subround(h, rc, iter, sg, q);
+  if (r != KMP_OK) {
+    return r;
+  }
+  const uint32_t cap = subround_cap(h, q);
+  k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, cap,
+                                                                      static_cast<uint32_t *>(d_send));
+  ++h->kernel_launches;
+  KMP_CUDA(cudaGetLastError());
+  return KMP_OK;
+}
+
+// Commit sub-round sg from the all-gathered proposal buffers (world * (4 + 2 * cap) words).
+int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void *d_gathered) {
+  if (h == nullptr || h->step_mode < 0 || d_gathered == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  const RunCtx rc{h->step_mode, h->step_labels, h->step_mcw, h->step_has_min, h->step_has_comm};
+  const SubRound q = subround_of_sg(h, sg);
+  const uint32_t cap = subround_cap(h, q);
+  const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(static_cast<const uint32_t *>(d_gathered), h->world,
+                                                                        cap, h->mv_u.p, h->mv_t.p, h->ctr32.p);
+  const uint32_t agrid = grid_for(q.size_a + q.size_b, 256, kSMs * 8);
+  if (rc.mode == 0) {
+    k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, h->vwgt, base_commit,
+                                                          h->incoming.p, h->hist.p);
+  } else {
+    k_accumulate_movers<1><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, h->vwgt, base_commit,
+                                                          h->incoming.p, h->hist.p);
+  }
+  h->kernel_launches += 2;
+  KMP_CUDA(cudaGetLastError());
+  return commit_subround(h, rc, iter, sg, q);
+}
+
+int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved) {
+  if (h == nullptr || moved == nullptr) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  uint32_t host[2] = {0, 0};
+  KMP_CUDA(cudaMemcpyAsync(host, h->ctr32.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  *moved = host[1];
+  return KMP_OK;
+}
+
+// favored[u] ^ u into / out of a caller-provided device buffer of n words (for a MAX all-reduce:
+// only the rank that owns u ever writes favored[u]; everybody else still holds u, i.e. 0 here).
+int kmp_lp_step_favored_export(kmp_lp_handle *h, void *d_buf) {
+  if (h == nullptr || d_buf == nullptr || h->step_mode != 0) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  k_xor_iota<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->favored.p, static_cast<uint32_t *>(d_buf));
+  KMP_CUDA(cudaGetLastError());
+  return KMP_OK;
+}
+int kmp_lp_step_favored_import(kmp_lp_handle *h, const void *d_buf) {
+  if (h == nullptr || d_buf == nullptr || h->step_mode != 0) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  k_xor_iota<<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, static_cast<const uint32_t *>(d_buf), h->favored.p);
+  KMP_CUDA(cudaGetLastError());
+  return KMP_OK;
+}
+
+// Post passes (clusterer) and result download; stats hold THIS rank's share of the scan counters.
+int kmp_lp_step_finish(kmp_lp_handle *h, uint32_t *labels_out, int32_t *block_weights_out, kmp_lp_stats *stats) {
+  if (h == nullptr || h->step_mode < 0) {
+    return fail(KMP_ERR_INVALID, "step_begin_* not called");
+  }
+  const uint32_t n = h->n;
+  if (stats != nullptr) {
+    std::memset(stats, 0, sizeof(*stats));
+  }
+  if (h->step_mode == 0 && n > 0) {
+    uint32_t num_clusters = 0;
+    reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
+    k_count_nonzero<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->weight.p, h->ctr32.p + 2);
+    KMP_CUDA(cudaMemcpyAsync(&num_clusters, h->ctr32.p + 2, 4, cudaMemcpyDeviceToHost, h->stream));
+    KMP_CUDA(cudaStreamSynchronize(h->stream));
+    if (stats != nullptr) {
+      stats->num_clusters = num_clusters;
+    }
+    int rc = cluster_post_passes(h, h->step_mcw, num_clusters, stats);
+    if (rc != KMP_OK) {
+      return rc;
+    }
+    ++h->call_counter;
+  }
+  if (labels_out != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(labels_out, h->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (block_weights_out != nullptr && h->step_mode == 1) {
+    KMP_CUDA(cudaMemcpyAsync(block_weights_out, h->weight.p, static_cast<size_t>(h->step_labels) * 4,
+                             cudaMemcpyDeviceToHost, h->stream));
+  }
+  h->step_mode = -1;
+  return end_call(h, stats);
 }
 
 } // extern "C"

@@ -137,6 +137,7 @@ struct SweepArgs {
   uint32_t *__restrict__ mv_u;
   uint32_t *__restrict__ mv_t;
   uint32_t *__restrict__ mover_count;
+  bool accumulate;                     // add to incoming[] / hist[] while emitting proposals
   int32_t *__restrict__ incoming;      // clusterer: [n]
   int32_t *__restrict__ hist;          // refiner: [k][16]
   unsigned long long *__restrict__ counters; // [0] edges scanned, [8] nodes visited (of this kernel tier)

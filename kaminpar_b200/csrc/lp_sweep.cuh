@@ -24,6 +24,9 @@ __device__ __forceinline__ void emit_proposal(const SweepArgs &a, uint32_t idx, 
                                               int32_t uw) {
   a.mv_u[idx] = u;
   a.mv_t[idx] = target;
+  if (!a.accumulate) {
+    return; // sharded run: incoming[] / hist[] are accumulated over the gathered proposals
+  }
   if (MODE == 0) {
     atomicAdd(&a.incoming[target], uw);
   } else {
@@ -618,6 +621,7 @@ struct HubArgs {
   const uint32_t *__restrict__ sel_begin; // per list entry: its first selection item
   Cand *__restrict__ part_best;           // per selection item
   Cand *__restrict__ part_fav;
+  uint32_t rank, world;                   // hub entry i is owned by rank i % world
 };
 constexpr uint32_t kSelPieceSlots = 8192;
 
@@ -637,6 +641,9 @@ __global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const Sw
   constexpr int kWarps = kChunkThreads / 32;
   for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x) {
     const uint32_t entry = hb.item_entry[it];
+    if (entry % hb.world != hb.rank) {
+      continue;
+    }
     const uint32_t u = a.list[entry];
     if (a.active != nullptr && a.active[u] == 0) {
       continue; // active[u] is cleared by phase 2b only
@@ -720,7 +727,7 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_p
     const uint32_t entry = hb.sel_entry[it];
     const uint32_t u = a.list[entry];
     Cand c = cand_none(), f = cand_none();
-    const bool act = a.active == nullptr || a.active[u] != 0;
+    const bool act = (entry % hb.world == hb.rank) && (a.active == nullptr || a.active[u] != 0);
     if (act) {
       const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
       const uint32_t own = a.label[u];
@@ -794,6 +801,9 @@ template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   unsigned long long edges = 0, nodes = 0;
   for (uint32_t i = warp; i < a.list_size; i += nwarps) {
+    if (i % hb.world != hb.rank) {
+      continue;
+    }
     const uint32_t u = a.list[i];
     if (a.active != nullptr) {
       int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
