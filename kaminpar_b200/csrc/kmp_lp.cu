@@ -142,6 +142,7 @@ struct kmp_lp_handle {
   uint32_t step_labels = 0;
   int32_t step_mcw = 0;
   bool step_has_min = false, step_has_comm = false;
+  bool stepping = false; // proposals are accumulated by kmp_lp_step_commit, not by the sweep kernels
 };
 
 namespace {
@@ -711,7 +712,7 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   sa.base_tie = sync_base(h->cfg.seed, h->call_counter, iter, SALT_TIE);
   sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
   sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-  sa.accumulate = h->world == 1;
+  sa.accumulate = !h->stepping;
   reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
   h->cur_subround = q.sr;
   sa.list = h->order.p + h->list_off[sg] + q.lo_a;
@@ -1506,7 +1507,9 @@ int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send
   }
   const RunCtx rc{h->step_mode, h->step_labels, h->step_mcw, h->step_has_min, h->step_has_comm};
   const SubRound q = subround_of_sg(h, sg);
+  h->stepping = true;
   int r = sweep_subround(h, rc, iter, sg, q);
+  h->stepping = false;
   if (r != KMP_OK) {
     return r;
   }
