@@ -162,7 +162,9 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out);
  * reference's distributed twin (kaminpar-dist/refinement/lp/lp_refiner.cc:119-222: local
  * perform_iteration per chunk, then label exchange) with NCCL instead of MPI. */
 int kmp_lp_set_shard(kmp_lp_handle *h, uint32_t rank, uint32_t world);
-int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream); /* run on the caller's stream (NCCL ordering) */
+/* Issue all work on the caller's stream (so that it is ordered with the caller's NCCL collectives).
+ * 0 = the legacy default stream; (void*)-1 = back to the handle's own stream. */
+int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream);
 uint32_t kmp_lp_num_subrounds(kmp_lp_handle *h);
 /* cap: proposals one rank can emit in sub-round sg (buffer = 4 + 2*cap words); size: vertices in it */
 int kmp_lp_subround_cap(kmp_lp_handle *h, uint32_t sg, uint32_t *cap_out, uint32_t *size_out);

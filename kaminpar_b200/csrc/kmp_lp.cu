@@ -1391,7 +1391,9 @@ int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream) {
     return fail(KMP_ERR_INVALID, "null handle");
   }
   KMP_CUDA(cudaStreamSynchronize(h->stream));
-  h->stream = cuda_stream != nullptr ? static_cast<cudaStream_t>(cuda_stream) : h->owned_stream;
+  // 0 is a valid handle (the legacy default stream, which is what torch uses unless told otherwise);
+  // (void*)-1 switches back to the handle's own stream
+  h->stream = cuda_stream == reinterpret_cast<void *>(-1) ? h->owned_stream : static_cast<cudaStream_t>(cuda_stream);
   return KMP_OK;
 }
 
