@@ -121,6 +121,7 @@ struct kmp_lp_handle {
   // tier 4 (deg >= 2048): per list entry the first slot of its global table region, and the
   // (entry, chunk) work items of phase 1; all per sub-round
   DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk, t4_sel_entry, t4_sel_piece, t4_sel_begin;
+  DevBuf<uint32_t> t4_item_u, t4_item_beg, t4_item_deg; // static per item: vertex, xadj[u], degree
   std::vector<uint32_t> t4_item_off, t4_sel_off; // S + 1
   DevBuf<Cand> t4_part_best, t4_part_fav;
   uint64_t t4_max_slots = 0;
@@ -175,10 +176,13 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32
   }
 }
 
-__global__ void k_gather_degrees(uint32_t cnt, const uint32_t *list, const uint32_t *xadj, uint32_t *deg) {
+__global__ void k_gather_degrees(uint32_t cnt, const uint32_t *list, const uint32_t *xadj, uint32_t *deg, uint32_t *beg,
+                                 uint32_t *ids) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
     const uint32_t u = list[i];
     deg[i] = xadj[u + 1] - xadj[u];
+    beg[i] = xadj[u];
+    ids[i] = u;
   }
 }
 
@@ -391,13 +395,16 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     const uint32_t s_idx = h->cur_subround;
     hb.item_entry = h->t4_item_entry.p + h->t4_item_off[s_idx];
     hb.item_chunk = h->t4_item_chunk.p + h->t4_item_off[s_idx];
+    hb.item_u = h->t4_item_u.p + h->t4_item_off[s_idx];
+    hb.item_beg = h->t4_item_beg.p + h->t4_item_off[s_idx];
+    hb.item_deg = h->t4_item_deg.p + h->t4_item_off[s_idx];
     hb.num_items = h->t4_item_off[s_idx + 1] - h->t4_item_off[s_idx];
     hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
     hb.g_tab = h->hub_tab.p;
     hb.rank = h->rank;
     hb.world = h->world;
     if (hb.num_items > 0) {
-      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 24), kChunkThreads, 0, h->stream>>>(a, hb);
+      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 6), kChunkThreads, 0, h->stream>>>(a, hb, h->m);
     }
     hb.sel_entry = h->t4_sel_entry.p + h->t4_sel_off[s_idx];
     hb.sel_piece = h->t4_sel_piece.p + h->t4_sel_off[s_idx];
@@ -506,15 +513,23 @@ int ensure_lists(kmp_lp_handle *h) {
     h->t4_item_off.assign(S + 1, 0);
     h->t4_max_slots = 0;
     if (t4_cnt > 0) {
-      DevBuf<uint32_t> d_deg;
+      DevBuf<uint32_t> d_deg, d_beg, d_ids;
       KMP_CUDA(d_deg.ensure(t4_cnt));
-      k_gather_degrees<<<grid_for(t4_cnt, 256), 256, 0, h->stream>>>(t4_cnt, h->order.p + t4_begin, h->xadj, d_deg.p);
+      KMP_CUDA(d_beg.ensure(t4_cnt));
+      KMP_CUDA(d_ids.ensure(t4_cnt));
+      k_gather_degrees<<<grid_for(t4_cnt, 256), 256, 0, h->stream>>>(t4_cnt, h->order.p + t4_begin, h->xadj, d_deg.p,
+                                                                      d_beg.p, d_ids.p);
+      std::vector<uint32_t> vbeg(t4_cnt), vids(t4_cnt), iu, ibeg, ideg;
+      KMP_CUDA(cudaMemcpyAsync(vbeg.data(), d_beg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(vids.data(), d_ids.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), sbeg(t4_cnt), ient, ichk, sent, spiece;
       h->t4_sel_off.assign(S + 1, 0);
       size_t max_sel = 0;
       KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       KMP_CUDA(cudaStreamSynchronize(h->stream));
       d_deg.release();
+      d_beg.release();
+      d_ids.release();
       for (uint32_t sr = 0; sr < S; ++sr) {
         const uint32_t lo = h->list_off[4 * S + sr] - t4_begin, hi = h->list_off[4 * S + sr + 1] - t4_begin;
         uint64_t slots = 0;
@@ -532,6 +547,9 @@ int ensure_lists(kmp_lp_handle *h) {
           for (uint32_t c = 0; c < chunks; ++c) {
             ient.push_back(i - lo);
             ichk.push_back(c);
+            iu.push_back(vids[i]);
+            ibeg.push_back(vbeg[i]);
+            ideg.push_back(deg[i]);
           }
           sbeg[i] = static_cast<uint32_t>(sent.size() - h->t4_sel_off[sr]);
           const uint32_t pieces = static_cast<uint32_t>((cap + kSelPieceSlots - 1) / kSelPieceSlots);
@@ -551,6 +569,12 @@ int ensure_lists(kmp_lp_handle *h) {
       KMP_CUDA(cudaMemcpyAsync(h->t4_table_off.p, toff.data(), t4_cnt * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(cudaMemcpyAsync(h->t4_item_entry.p, ient.data(), ient.size() * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(cudaMemcpyAsync(h->t4_item_chunk.p, ichk.data(), ichk.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(h->t4_item_u.ensure(iu.size()));
+      KMP_CUDA(h->t4_item_beg.ensure(iu.size()));
+      KMP_CUDA(h->t4_item_deg.ensure(iu.size()));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_item_u.p, iu.data(), iu.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_item_beg.p, ibeg.data(), iu.size() * 4, cudaMemcpyHostToDevice, h->stream));
+      KMP_CUDA(cudaMemcpyAsync(h->t4_item_deg.p, ideg.data(), iu.size() * 4, cudaMemcpyHostToDevice, h->stream));
       KMP_CUDA(h->t4_sel_entry.ensure(sent.size()));
       KMP_CUDA(h->t4_sel_piece.ensure(spiece.size()));
       KMP_CUDA(h->t4_sel_begin.ensure(t4_cnt));
@@ -989,11 +1013,6 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     cudaFuncSetAttribute(sweep_group<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
     cudaFuncSetAttribute(sweep_group<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
     cudaFuncSetAttribute(sweep_group<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-    const int smem_c = kChunkTableSlots * 8;
-    cudaFuncSetAttribute(sweep_hub_aggregate<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
-    cudaFuncSetAttribute(sweep_hub_aggregate<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
-    cudaFuncSetAttribute(sweep_hub_aggregate<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
-    cudaFuncSetAttribute(sweep_hub_aggregate<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c);
   }
   *out = h;
   return KMP_OK;

@@ -611,6 +611,9 @@ constexpr int kChunkThreads = 256;
 struct HubArgs {
   const uint32_t *__restrict__ item_entry; // index into the tier-4 list of this sub-round
   const uint32_t *__restrict__ item_chunk;
+  const uint32_t *__restrict__ item_u;   // static per item: vertex id, xadj[u], degree
+  const uint32_t *__restrict__ item_beg;
+  const uint32_t *__restrict__ item_deg;
   uint32_t num_items;
   const uint32_t *__restrict__ table_off;  // per list entry: first slot of its region
   unsigned long long *__restrict__ g_tab; // packed entries
@@ -631,88 +634,183 @@ __device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_l
   return cap < 32 ? 32 : cap;
 }
 
+// ---- 1-D bulk TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct HubItem {
+  uint32_t valid;   // 0: nothing to do for this item
+  uint32_t u;
+  uint32_t entry;
+  uint32_t full_deg;
+  uint32_t gbeg, gend; // edge range of the chunk (indices into adjncy)
+  uint32_t a0;         // first staged element (gbeg rounded down to a 16-byte boundary)
+  uint32_t staged;     // number of staged elements (multiple of 4), may stop short of gend at the array end
+};
+
 template <int MODE, bool EW>
-__global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb) {
-  // No shared-memory table: the 32 neighbour labels a warp loads together are de-duplicated with
-  // match.any (later LP rounds: most neighbours of a hub share a few labels), the leader of each
-  // group merges the group's rating into the vertex's global region with one 64-bit atomic.
+__global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
+  // Phase 1 of tier 4. The 2048-edge chunk of the hub's adjacency is staged into shared memory
+  // with ONE bulk TMA copy (cp.async.bulk + mbarrier), double-buffered: the copy of the next item
+  // is in flight while the current one is processed. The 32 neighbour labels a warp gathers
+  // together are de-duplicated with match.any (later LP rounds: most neighbours of a hub share a few
+  // labels); the leader of each group merges the group's rating into the vertex's global region
+  // with one 64-bit atomic.
+  __shared__ __align__(16) uint32_t s_adj[2][kChunkEdges + 8];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ HubItem s_item[2];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   constexpr int kWarps = kChunkThreads / 32;
-  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x) {
-    const uint32_t entry = hb.item_entry[it];
-    if (entry % hb.world != hb.rank) {
-      continue;
-    }
-    const uint32_t u = a.list[entry];
-    if (a.active != nullptr && a.active[u] == 0) {
-      continue; // active[u] is cleared by phase 2b only
-    }
-    const uint32_t beg0 = a.xadj[u];
-    const uint32_t full_deg = a.xadj[u + 1] - beg0;
-    uint32_t deg = full_deg;
-    if (deg > a.max_num_neighbors) {
-      deg = a.max_num_neighbors;
-    }
-    const uint32_t cbeg = hb.item_chunk[it] * kChunkEdges;
-    if (cbeg >= deg) {
-      continue;
-    }
-    const uint32_t cend = (cbeg + kChunkEdges < deg) ? cbeg + kChunkEdges : deg;
-    if (MODE == 1) {
-      const uint32_t own = a.label[u];
-      const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
-      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
-      if ((a.weight[own] - uw) < mn) {
-        continue; // lp_refiner.cc:160-162: no ratings needed
-      }
-    }
-    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
-    const bool gdirect = a.num_labels <= gcap;
-    unsigned long long *gt = hb.g_tab + hb.table_off[entry];
-    // each warp takes batches of 4 x 32 consecutive edges
-    for (uint32_t e0 = cbeg + wib * 128; e0 < cend; e0 += kWarps * 128) {
-      uint32_t k4[4];
-      int32_t w4[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { // 4 independent gathers per lane in flight
-        const uint32_t e = e0 + j * 32 + lane;
-        k4[j] = kEmpty;
-        w4[j] = 0;
-        if (e < cend) {
-          const uint32_t v = a.adjncy[beg0 + e];
-          bool ok = true;
-          if (MODE == 1 && a.communities != nullptr) {
-            ok = a.communities[u] == a.communities[v];
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // thread 0: evaluate item `it`, publish its descriptor and start the bulk copy into `stage`
+  auto prepare = [&](uint32_t it, int stage) {
+    HubItem d{};
+    d.valid = 0;
+    if (it < hb.num_items) {
+      const uint32_t entry = hb.item_entry[it]; // the five descriptor loads are independent
+      const uint32_t u = hb.item_u[it];
+      const uint32_t beg0 = hb.item_beg[it];
+      const uint32_t full_deg = hb.item_deg[it];
+      if (entry % hb.world == hb.rank) {
+        if (a.active == nullptr || a.active[u] != 0) {
+          uint32_t deg = full_deg;
+          if (deg > a.max_num_neighbors) {
+            deg = a.max_num_neighbors;
+          }
+          const uint32_t cbeg = hb.item_chunk[it] * kChunkEdges;
+          bool ok = cbeg < deg;
+          if (ok && MODE == 1) {
+            const uint32_t own = a.label[u];
+            const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+            const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+            ok = !((a.weight[own] - uw) < mn); // lp_refiner.cc:160-162: no ratings needed
           }
           if (ok) {
-            k4[j] = a.label[v];
-            w4[j] = EW ? a.adjwgt[beg0 + e] : 1;
+            const uint32_t cend = (cbeg + kChunkEdges < deg) ? cbeg + kChunkEdges : deg;
+            d.valid = 1;
+            d.u = u;
+            d.entry = entry;
+            d.full_deg = full_deg;
+            d.gbeg = beg0 + cbeg;
+            d.gend = beg0 + cend;
+            d.a0 = d.gbeg & ~3u;
+            uint32_t a1 = (d.gend + 3u) & ~3u;
+            const uint32_t m4 = m_total & ~3u; // last 16-byte block that lies fully inside adjncy
+            if (a1 > m4) {
+              a1 = m4;
+            }
+            d.staged = a1 > d.a0 ? a1 - d.a0 : 0;
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned peers = __match_any_sync(kFull, k4[j]);
-        int32_t r;
-        if (EW) {
-          r = 0;
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int32_t wq = __shfl_sync(kFull, w4[j], q);
-            r += ((peers >> q) & 1u) ? wq : 0;
-          }
-        } else {
-          r = __popc(peers);
-        }
-        const bool leader = lane == __ffs(peers) - 1;
-        if (!leader) {
-          k4[j] = kEmpty;
-        }
-        w4[j] = r;
-      }
-      table64_add_batch<4>(gt, gcap - 1, gdirect, k4, w4);
     }
+    s_item[stage] = d;
+    if (d.valid && d.staged > 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the buffer are done
+      mbar_arrive_expect_tx(&s_bar[stage], d.staged * 4);
+      tma_load_1d(&s_adj[stage][0], a.adjncy + d.a0, d.staged * 4, &s_bar[stage]);
+    }
+  };
+
+  uint32_t uses[2] = {0, 0};
+  if (threadIdx.x == 0) {
+    prepare(blockIdx.x, 0);
+  }
+  __syncthreads();
+  int stage = 0;
+  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, stage ^= 1) {
+    if (threadIdx.x == 0) {
+      prepare(it + gridDim.x, stage ^ 1); // prefetch the next item of this CTA
+    }
+    const HubItem d = s_item[stage];
+    if (d.valid) {
+      if (d.staged > 0) {
+        mbar_wait(&s_bar[stage], uses[stage] & 1u);
+        ++uses[stage];
+      }
+      const uint32_t gcap = hub_cap(d.full_deg, a.num_labels);
+      const bool gdirect = a.num_labels <= gcap;
+      unsigned long long *gt = hb.g_tab + hb.table_off[d.entry];
+      const uint32_t staged_end = d.a0 + d.staged;
+      // each warp takes batches of 4 x 32 consecutive edges
+      for (uint32_t e0 = d.gbeg + wib * 128; e0 < d.gend; e0 += kWarps * 128) {
+        uint32_t k4[4];
+        int32_t w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { // 4 independent label gathers per lane in flight
+          const uint32_t e = e0 + j * 32 + lane;
+          k4[j] = kEmpty;
+          w4[j] = 0;
+          if (e < d.gend) {
+            const uint32_t v = e < staged_end ? s_adj[stage][e - d.a0] : a.adjncy[e];
+            bool ok = true;
+            if (MODE == 1 && a.communities != nullptr) {
+              ok = a.communities[d.u] == a.communities[v];
+            }
+            if (ok) {
+              k4[j] = a.label[v];
+              w4[j] = EW ? a.adjwgt[e] : 1;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned peers = __match_any_sync(kFull, k4[j]);
+          int32_t r;
+          if (EW) {
+            r = 0;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int32_t wq = __shfl_sync(kFull, w4[j], q);
+              r += ((peers >> q) & 1u) ? wq : 0;
+            }
+          } else {
+            r = __popc(peers);
+          }
+          const bool leader = lane == __ffs(peers) - 1;
+          if (!leader) {
+            k4[j] = kEmpty;
+          }
+          w4[j] = r;
+        }
+        table64_add_batch<4>(gt, gcap - 1, gdirect, k4, w4);
+      }
+    }
+    __syncthreads(); // everybody is done with s_adj[stage] / s_item[stage]; s_item[stage ^ 1] is visible
   }
 }
 

@@ -14,7 +14,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref.so")          # serial stand-in: deterministic, pins the oracle
+REF_OMP_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref_omp.so")  # OpenMP stand-in: all host cores (CPU baseline)
 ORACLE_LIB = os.path.join(_HERE, "liblp_oracle.so")
 
 U32P = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
@@ -107,10 +108,26 @@ def ref_rearrange(g, remove_isolated=True):
     return out, o2n
 
 
-def ref_lp_cluster(g, seed, max_cluster_weight, desired=0, params=None, num_calls=1):
+_ref_omp = None
+
+
+def have_parallel_reference() -> bool:
+    return os.path.exists(REF_OMP_LIB)
+
+
+def ref_omp():
+    global _ref_omp
+    if _ref_omp is None:
+        _ref_omp = C.CDLL(REF_OMP_LIB)
+    return _ref_omp
+
+
+def ref_lp_cluster(g, seed, max_cluster_weight, desired=0, params=None, num_calls=1, parallel=False):
+    """parallel=True: the same unmodified sources on all host cores (OpenMP mode of the stand-in);
+    like the reference with T > 1 threads the result then depends on thread timing."""
     params = params or default_cluster_params()
     out = np.zeros(g.n * num_calls, np.uint32)
-    ref().kmpref_lp_cluster(
+    (ref_omp() if parallel else ref()).kmpref_lp_cluster(
         *_garrs(g), C.c_int(1 if g.sorted else 0), C.c_int(seed), C.c_int32(max_cluster_weight),
         C.c_uint32(desired), C.byref(params), C.c_int(num_calls), out.ctypes.data_as(C.c_void_p),
     )

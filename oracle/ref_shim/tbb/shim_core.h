@@ -14,6 +14,16 @@
 // arena in which KaMinPar runs its algorithms.
 #pragma once
 
+// Two build modes:
+//   default              : serial (deterministic; used to pin the oracle, oracle/_ref/libkaminpar_ref.so)
+//   -DKMP_SHIM_PARALLEL  : parallel_for / enumerable_thread_specific / concurrent_vector backed by OpenMP
+//                          threads, so that the reference's LP runs on all host cores for the CPU
+//                          baseline (oracle/_ref/libkaminpar_ref_omp.so). Like with real oneTBB the
+//                          result then depends on thread timing.
+#ifdef KMP_SHIM_PARALLEL
+#include <omp.h>
+#endif
+
 #include <algorithm>
 #include <cstddef>
 #include <cstdlib>
@@ -56,6 +66,44 @@ struct simple_partitioner {};
 struct static_partitioner {};
 
 // ---- parallel_for ---------------------------------------------------------------------------
+namespace shim_detail {
+#ifdef KMP_SHIM_PARALLEL
+inline bool in_parallel() { return omp_in_parallel() != 0; }
+inline int num_threads() { return omp_get_max_threads(); }
+inline int thread_index() { return omp_get_thread_num(); }
+#else
+inline bool in_parallel() { return true; }
+inline int num_threads() { return 1; }
+inline int thread_index() { return 0; }
+#endif
+} // namespace shim_detail
+
+template <typename Value, typename Body> void parallel_for(const blocked_range<Value> &range, const Body &body) {
+  if (range.empty()) {
+    return;
+  }
+#ifdef KMP_SHIM_PARALLEL
+  if constexpr (std::is_integral_v<Value>) {
+    if (!shim_detail::in_parallel() && shim_detail::num_threads() > 1) {
+      const std::size_t n = range.size();
+      const std::size_t target = (n + 8 * shim_detail::num_threads() - 1) / (8 * shim_detail::num_threads());
+      const std::size_t grain = std::max<std::size_t>(std::max<std::size_t>(range.grainsize(), 1), target);
+      const std::size_t chunks = (n + grain - 1) / grain;
+#pragma omp parallel for schedule(dynamic, 1)
+      for (std::size_t c = 0; c < chunks; ++c) {
+        const Value b = static_cast<Value>(range.begin() + c * grain);
+        const Value e = static_cast<Value>(std::min<std::size_t>(n, (c + 1) * grain) + range.begin());
+        body(blocked_range<Value>(b, e, range.grainsize()));
+      }
+      return;
+    }
+  }
+#endif
+  body(range);
+}
+
+// any other range type (e.g. enumerable_thread_specific::range_type): one sequential call; the
+// blocked_range overload above is more specialised and wins for blocked ranges
 template <typename Range, typename Body,
           typename = decltype(std::declval<const Range &>().begin())>
 void parallel_for(const Range &range, const Body &body) {
@@ -74,6 +122,17 @@ void parallel_for(const Range &range, const Body &body, const Partitioner &) {
 template <typename Index, typename Function,
           typename = std::enable_if_t<std::is_integral_v<Index>>>
 void parallel_for(Index first, Index last, const Function &f) {
+#ifdef KMP_SHIM_PARALLEL
+  if (!shim_detail::in_parallel() && shim_detail::num_threads() > 1 && first < last) {
+    const long long n = static_cast<long long>(last) - static_cast<long long>(first);
+    const long long chunk = std::max<long long>(1, n / (16LL * shim_detail::num_threads()));
+#pragma omp parallel for schedule(dynamic, chunk)
+    for (long long i = 0; i < n; ++i) {
+      f(static_cast<Index>(first + i));
+    }
+    return;
+  }
+#endif
   for (Index i = first; i < last; ++i) {
     f(i);
   }
@@ -131,8 +190,8 @@ Value parallel_scan(const Range &range, const Value &identity, const Scan &scan,
 
 // ---- arena ----------------------------------------------------------------------------------
 namespace this_task_arena {
-inline int max_concurrency() { return 1; }
-inline int current_thread_index() { return 0; }
+inline int max_concurrency() { return shim_detail::num_threads(); }
+inline int current_thread_index() { return shim_detail::thread_index(); }
 template <typename F> auto isolate(F &&f) { return f(); }
 } // namespace this_task_arena
 
@@ -267,7 +326,7 @@ public:
 
   enumerable_thread_specific(enumerable_thread_specific &&) noexcept = default;
   enumerable_thread_specific &operator=(enumerable_thread_specific &&) noexcept = default;
-  enumerable_thread_specific(const enumerable_thread_specific &o) : _init(o._init) {
+  enumerable_thread_specific(const enumerable_thread_specific &o) : _init(o._init) {  // slots copied, thread map rebuilt lazily
     for (const auto &p : o._slots) {
       if constexpr (std::is_copy_constructible_v<T>) {
         _slots.push_back(std::make_unique<T>(*p));
@@ -283,19 +342,48 @@ public:
   }
 
   reference local() {
+#ifdef KMP_SHIM_PARALLEL
+    const int t = shim_detail::thread_index();
+    if (_by_thread.empty()) {
+#pragma omp critical(kmp_shim_ets)
+      {
+        if (_by_thread.empty()) {
+          _by_thread.assign(static_cast<std::size_t>(shim_detail::num_threads()) + 1, nullptr);
+        }
+      }
+    }
+    T *p = _by_thread[static_cast<std::size_t>(t)];
+    if (p == nullptr) {
+      std::unique_ptr<T> fresh = _init();
+      p = fresh.get();
+#pragma omp critical(kmp_shim_ets)
+      { _slots.push_back(std::move(fresh)); }
+      _by_thread[static_cast<std::size_t>(t)] = p;
+    }
+    return *p;
+#else
     if (_slots.empty()) {
       _slots.push_back(_init());
     }
     return *_slots.front();
+#endif
   }
   reference local(bool &exists) {
+#ifdef KMP_SHIM_PARALLEL
+    const int t = shim_detail::thread_index();
+    exists = !_by_thread.empty() && _by_thread[static_cast<std::size_t>(t)] != nullptr;
+#else
     exists = !_slots.empty();
+#endif
     return local();
   }
 
   std::size_t size() const { return _slots.size(); }
   bool empty() const { return _slots.empty(); }
-  void clear() { _slots.clear(); }
+  void clear() {
+    _slots.clear();
+    _by_thread.clear();
+  }
 
   it_type begin() { return it_type(_slots.begin()); }
   it_type end() { return it_type(_slots.end()); }
@@ -324,6 +412,7 @@ public:
 private:
   std::function<std::unique_ptr<T>()> _init;
   std::vector<std::unique_ptr<T>> _slots;
+  std::vector<T *> _by_thread; // parallel mode: slot of each OpenMP thread
 };
 
 // ---- combinable -----------------------------------------------------------------------------
@@ -377,17 +466,40 @@ public:
     iterator _b, _e;
   };
 
+  // growth is serialised; like with tbb::concurrent_vector callers must not rely on iterators
+  // obtained before a concurrent growth
   iterator push_back(const T &v) {
-    base::push_back(v);
-    return base::end() - 1;
+    iterator it;
+#ifdef KMP_SHIM_PARALLEL
+#pragma omp critical(kmp_shim_cvec)
+#endif
+    {
+      base::push_back(v);
+      it = base::end() - 1;
+    }
+    return it;
   }
   iterator push_back(T &&v) {
-    base::push_back(std::move(v));
-    return base::end() - 1;
+    iterator it;
+#ifdef KMP_SHIM_PARALLEL
+#pragma omp critical(kmp_shim_cvec)
+#endif
+    {
+      base::push_back(std::move(v));
+      it = base::end() - 1;
+    }
+    return it;
   }
   template <typename... Args> iterator emplace_back(Args &&...args) {
-    base::emplace_back(std::forward<Args>(args)...);
-    return base::end() - 1;
+    iterator it;
+#ifdef KMP_SHIM_PARALLEL
+#pragma omp critical(kmp_shim_cvec)
+#endif
+    {
+      base::emplace_back(std::forward<Args>(args)...);
+      it = base::end() - 1;
+    }
+    return it;
   }
   iterator grow_by(std::size_t delta) {
     const std::size_t old = base::size();
