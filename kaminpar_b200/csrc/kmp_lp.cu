@@ -143,6 +143,7 @@ struct kmp_lp_handle {
   uint32_t step_labels = 0;
   int32_t step_mcw = 0;
   bool step_has_min = false, step_has_comm = false;
+  uint32_t mover_parity = 0; // proposal counter in use: ctr32[0] (parity 0) or ctr32[3] (parity 1)
   bool stepping = false; // proposals are accumulated by kmp_lp_step_commit, not by the sweep kernels
 };
 
@@ -404,7 +405,7 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     hb.rank = h->rank;
     hb.world = h->world;
     if (hb.num_items > 0) {
-      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 6), kChunkThreads, 0, h->stream>>>(a, hb, h->m);
+      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
     }
     hb.sel_entry = h->t4_sel_entry.p + h->t4_sel_off[s_idx];
     hb.sel_piece = h->t4_sel_piece.p + h->t4_sel_off[s_idx];
@@ -666,7 +667,7 @@ SweepArgs make_sweep_args(kmp_lp_handle *h, const RunCtx &rc) {
   a.max_num_neighbors = h->cfg.max_num_neighbors;
   a.mv_u = h->mv_u.p;
   a.mv_t = h->mv_t.p;
-  a.mover_count = h->ctr32.p;
+  a.mover_count = h->ctr32.p + (h->mover_parity ? 3 : 0);
   a.incoming = h->incoming.p;
   a.hist = h->hist.p;
   a.counters = h->ctr64.p;
@@ -690,7 +691,8 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
   c.mv_u = h->mv_u.p;
   c.mv_t = h->mv_t.p;
   c.acc = h->acc.p;
-  c.mover_count = h->ctr32.p;
+  c.mover_count = h->ctr32.p + (h->mover_parity ? 3 : 0);
+  c.next_mover_count = h->ctr32.p + (h->mover_parity ? 0 : 3);
   c.incoming = h->incoming.p;
   c.slotmap = h->slotmap.p;
   c.cslot = h->cslot.p;
@@ -737,7 +739,6 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
   sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   sa.accumulate = !h->stepping;
-  reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p);
   h->cur_subround = q.sr;
   sa.list = h->order.p + h->list_off[sg] + q.lo_a;
   sa.list_size = q.hi_a - q.lo_a;
@@ -760,11 +761,10 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
   if (rc.mode == 0) {
     commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
     commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
-    commit_apply<0><<<cgrid, 256, 0, h->stream>>>(ca);
-    h->kernel_launches += 4;
+    h->kernel_launches += 3;
   } else {
     const uint32_t kgrid = grid_for(rc.num_labels, 128);
-    commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p);
+    commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p + (h->mover_parity ? 3 : 0));
     commit_refine_prepare<<<kgrid, 128, 0, h->stream>>>(ca);
     for (uint32_t p = 0; p < passes; ++p) {
       commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
@@ -777,17 +777,23 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
       commit_refine_othin<<<cgrid, 256, 0, h->stream>>>(ca);
       h->kernel_launches += 3;
     }
-    commit_apply<1><<<cgrid, 256, 0, h->stream>>>(ca);
     commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
     h->kernel_launches += 2;
   }
-  switch (q.group) {
-  case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  // apply + activate in one launch; it also zeroes the other proposal counter for the next sub-round
+  const int variant = (rc.mode == 0 ? 0 : 4) + (q.group > 3 ? 3 : q.group);
+  switch (variant) {
+  case 0: commit_apply_activate<0, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 1: commit_apply_activate<0, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 2: commit_apply_activate<0, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 3: commit_apply_activate<0, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
   }
   h->kernel_launches += 1;
+  h->mover_parity ^= 1u;
   KMP_CUDA(cudaGetLastError());
   return KMP_OK;
 }
@@ -795,7 +801,8 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
 int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
   const uint32_t S = h->lists_S;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // mover, moved, proposals
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // both proposal counters, moved
+  h->mover_parity = 0;
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
     const SubRound q = subround_of_sg(h, sg);
     if (q.size_a + q.size_b == 0) {
@@ -1517,6 +1524,7 @@ int kmp_lp_step_begin_iteration(kmp_lp_handle *h) {
     return fail(KMP_ERR_INVALID, "step_begin_* not called");
   }
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream));
+  h->mover_parity = 0;
   return KMP_OK;
 }
 
@@ -1535,7 +1543,8 @@ int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send
     return r;
   }
   const uint32_t cap = subround_cap(h, q);
-  k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, cap,
+  k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p,
+                                                                      h->ctr32.p + (h->mover_parity ? 3 : 0), cap,
                                                                       static_cast<uint32_t *>(d_send));
   ++h->kernel_launches;
   KMP_CUDA(cudaGetLastError());
@@ -1552,13 +1561,13 @@ int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void 
   const uint32_t cap = subround_cap(h, q);
   const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(static_cast<const uint32_t *>(d_gathered), h->world,
-                                                                        cap, h->mv_u.p, h->mv_t.p, h->ctr32.p);
+                                                                        cap, h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0));
   const uint32_t agrid = grid_for(q.size_a + q.size_b, 256, kSMs * 8);
   if (rc.mode == 0) {
-    k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, h->vwgt, base_commit,
+    k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
                                                           h->incoming.p, h->hist.p);
   } else {
-    k_accumulate_movers<1><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p, h->vwgt, base_commit,
+    k_accumulate_movers<1><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
                                                           h->incoming.p, h->hist.p);
   }
   h->kernel_launches += 2;

@@ -30,6 +30,7 @@ struct CommitArgs {
   const uint32_t *__restrict__ mv_t;
   uint8_t *__restrict__ acc; // 0 rejected/pending, 1 accepted, 2 contended-pending (clusterer)
   const uint32_t *__restrict__ mover_count;
+  uint32_t *__restrict__ next_mover_count; // zeroed for the following sub-round
   uint32_t base_commit;
   // clusterer
   int32_t *__restrict__ incoming; // [n]
@@ -195,34 +196,54 @@ __global__ void commit_refine_reset(const CommitArgs a) {
   }
 }
 
-// ---- apply (both modes): weights, labels, scratch clean-up -----------------------------------
-template <int MODE> __global__ void commit_apply(const CommitArgs a) {
+// ---- apply + activate (both modes) ------------------------------------------------------------
+// A team of LANES threads (4, 8, 32 or the whole 256-thread CTA, by the degree group of the
+// sub-round) handles one proposal: lane 0 applies it (label, weights, commit-scratch clean-up;
+// label_propagation.h:826-834) and, if it was accepted, the team flags the neighbours of the moved
+// vertex as active (label_propagation.h:848-870). Rejected proposals stay active for the next
+// round. Thread 0 of the grid also zeroes the proposal counter of the NEXT sub-round.
+template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_apply_activate(const CommitArgs a) {
   const uint32_t cnt = *a.mover_count;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sub = tid % LANES;
+  const uint32_t nteams = (gridDim.x * blockDim.x) / LANES;
+  if (tid == 0) {
+    *a.next_mover_count = 0;
+  }
   uint32_t moved = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+  for (uint32_t i = tid / LANES; i < cnt; i += nteams) {
     const uint32_t u = a.mv_u[i];
-    const uint32_t t = a.mv_t[i];
     const uint8_t acc = a.acc[i];
-    if (MODE == 0) {
-      a.incoming[t] = 0; // every proposer of t writes the same value
-      if (a.slotmap[t] == i) { // slot owner cleans the contended-target scratch
-        int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
+    if (sub == 0) {
+      const uint32_t t = a.mv_t[i];
+      if (MODE == 0) {
+        a.incoming[t] = 0; // every proposer of t writes the same value
+        if (a.slotmap[t] == i) { // slot owner cleans the contended-target scratch
+          int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
 #pragma unroll
-        for (int j = 0; j < kLadderLevels; ++j) {
-          h[j] = 0;
+          for (int j = 0; j < kLadderLevels; ++j) {
+            h[j] = 0;
+          }
+          a.slotmap[t] = kEmpty;
         }
-        a.slotmap[t] = kEmpty;
+      }
+      if (acc == 1) {
+        const int32_t w = node_weight(a, u);
+        const uint32_t from = a.label[u];
+        atomicAdd(&a.weight[t], w);
+        atomicSub(&a.weight[from], w);
+        a.label[u] = t;
+        ++moved;
+      } else {
+        a.active[u] = 1; // rejected proposals retry in the next round
       }
     }
     if (acc == 1) {
-      const int32_t w = node_weight(a, u);
-      const uint32_t from = a.label[u];
-      atomicAdd(&a.weight[t], w);
-      atomicSub(&a.weight[from], w);
-      a.label[u] = t;
-      ++moved;
-    } else {
-      a.active[u] = 1; // rejected proposals retry in the next round
+      const uint32_t beg = a.xadj[u];
+      const uint32_t end = a.xadj[u + 1];
+      for (uint32_t e = beg + sub; e < end; e += LANES) {
+        a.active[a.adjncy[e]] = 1;
+      }
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -230,27 +251,6 @@ template <int MODE> __global__ void commit_apply(const CommitArgs a) {
   }
   if ((threadIdx.x & 31) == 0 && moved != 0) {
     atomicAdd(a.moved_count, moved);
-  }
-}
-
-// ---- activate neighbours of moved vertices (label_propagation.h:848-870) ----------------------
-// LANES threads cooperate on one accepted proposal (LANES = 4, 8, 32 or the whole 256-thread CTA,
-// chosen by the degree group of the sub-round).
-template <int LANES> __global__ void __launch_bounds__(256) commit_activate(const CommitArgs a) {
-  const uint32_t cnt = *a.mover_count;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t sub = tid % LANES;
-  const uint32_t nteams = (gridDim.x * blockDim.x) / LANES;
-  for (uint32_t i = tid / LANES; i < cnt; i += nteams) {
-    if (a.acc[i] != 1) {
-      continue;
-    }
-    const uint32_t u = a.mv_u[i];
-    const uint32_t beg = a.xadj[u];
-    const uint32_t end = a.xadj[u + 1];
-    for (uint32_t e = beg + sub; e < end; e += LANES) {
-      a.active[a.adjncy[e]] = 1;
-    }
   }
 }
 // acc[] must start at 0 for the refiner's multi-pass decide; clear it and the counters

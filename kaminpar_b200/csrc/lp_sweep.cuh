@@ -675,43 +675,60 @@ struct HubItem {
   uint32_t staged;     // number of staged elements (multiple of 4), may stop short of gend at the array end
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kHubStages = 3;
+constexpr int kHubConsumerWarps = kChunkThreads / 32;          // 8 consumer warps
+constexpr int kHubThreads = kChunkThreads + 32;                // + 1 producer warp
+
 template <int MODE, bool EW>
-__global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
-  // Phase 1 of tier 4. The 2048-edge chunk of the hub's adjacency is staged into shared memory
-  // with ONE bulk TMA copy (cp.async.bulk + mbarrier), double-buffered: the copy of the next item
-  // is in flight while the current one is processed. The 32 neighbour labels a warp gathers
-  // together are de-duplicated with match.any (later LP rounds: most neighbours of a hub share a few
-  // labels); the leader of each group merges the group's rating into the vertex's global region
-  // with one 64-bit atomic.
-  __shared__ __align__(16) uint32_t s_adj[2][kChunkEdges + 8];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ HubItem s_item[2];
+__global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
+  // Phase 1 of tier 4, warp-specialised producer / consumer pipeline (3 stages):
+  //   producer warp : evaluates the next work item (2048-edge chunk of a hub's adjacency), publishes
+  //                   its descriptor and stages the chunk into shared memory with ONE bulk TMA copy
+  //                   (cp.async.bulk, completion on the stage's `full` mbarrier);
+  //   consumer warps: wait on `full`, gather the neighbour labels (4 independent gathers per lane),
+  //                   de-duplicate the 32 labels of a warp-batch with match.any and merge each
+  //                   group's rating into the vertex's global table region with one 64-bit atomic;
+  //                   then release the stage through the `empty` mbarrier.
+  __shared__ __align__(16) uint32_t s_adj[kHubStages][kChunkEdges + 8];
+  __shared__ __align__(8) uint64_t s_full[kHubStages];
+  __shared__ __align__(8) uint64_t s_empty[kHubStages];
+  __shared__ HubItem s_item[kHubStages];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  constexpr int kWarps = kChunkThreads / 32;
   if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+    for (int s = 0; s < kHubStages; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kHubConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // thread 0: evaluate item `it`, publish its descriptor and start the bulk copy into `stage`
-  auto prepare = [&](uint32_t it, int stage) {
-    HubItem d{};
-    d.valid = 0;
-    if (it < hb.num_items) {
-      const uint32_t entry = hb.item_entry[it]; // the five descriptor loads are independent
-      const uint32_t u = hb.item_u[it];
-      const uint32_t beg0 = hb.item_beg[it];
-      const uint32_t full_deg = hb.item_deg[it];
-      if (entry % hb.world == hb.rank) {
-        if (a.active == nullptr || a.active[u] != 0) {
+  if (wib == kHubConsumerWarps) {
+    // ------------------------------- producer warp -------------------------------------------
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, ++k) {
+        const int stage = static_cast<int>(k % kHubStages);
+        const uint32_t round = k / kHubStages;
+        mbar_wait(&s_empty[stage], (round & 1u) ^ 1u); // passes immediately in the first round
+        HubItem d{};
+        d.valid = 0;
+        const uint32_t entry = hb.item_entry[it]; // the descriptor loads are independent
+        const uint32_t u = hb.item_u[it];
+        const uint32_t beg0 = hb.item_beg[it];
+        const uint32_t full_deg = hb.item_deg[it];
+        const uint32_t chunk = hb.item_chunk[it];
+        if (entry % hb.world == hb.rank && (a.active == nullptr || a.active[u] != 0)) {
           uint32_t deg = full_deg;
           if (deg > a.max_num_neighbors) {
             deg = a.max_num_neighbors;
           }
-          const uint32_t cbeg = hb.item_chunk[it] * kChunkEdges;
+          const uint32_t cbeg = chunk * kChunkEdges;
           bool ok = cbeg < deg;
           if (ok && MODE == 1) {
             const uint32_t own = a.label[u];
@@ -736,38 +753,32 @@ __global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const Sw
             d.staged = a1 > d.a0 ? a1 - d.a0 : 0;
           }
         }
+        s_item[stage] = d;
+        if (d.valid && d.staged > 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive_expect_tx(&s_full[stage], d.staged * 4);
+          tma_load_1d(&s_adj[stage][0], a.adjncy + d.a0, d.staged * 4, &s_full[stage]);
+        } else {
+          mbar_arrive(&s_full[stage]); // nothing staged: publish the descriptor only
+        }
       }
     }
-    s_item[stage] = d;
-    if (d.valid && d.staged > 0) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // earlier generic reads of the buffer are done
-      mbar_arrive_expect_tx(&s_bar[stage], d.staged * 4);
-      tma_load_1d(&s_adj[stage][0], a.adjncy + d.a0, d.staged * 4, &s_bar[stage]);
-    }
-  };
-
-  uint32_t uses[2] = {0, 0};
-  if (threadIdx.x == 0) {
-    prepare(blockIdx.x, 0);
+    return;
   }
-  __syncthreads();
-  int stage = 0;
-  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, stage ^= 1) {
-    if (threadIdx.x == 0) {
-      prepare(it + gridDim.x, stage ^ 1); // prefetch the next item of this CTA
-    }
+
+  // --------------------------------- consumer warps ----------------------------------------------
+  uint32_t k = 0;
+  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, ++k) {
+    const int stage = static_cast<int>(k % kHubStages);
+    const uint32_t round = k / kHubStages;
+    mbar_wait(&s_full[stage], round & 1u);
     const HubItem d = s_item[stage];
     if (d.valid) {
-      if (d.staged > 0) {
-        mbar_wait(&s_bar[stage], uses[stage] & 1u);
-        ++uses[stage];
-      }
       const uint32_t gcap = hub_cap(d.full_deg, a.num_labels);
       const bool gdirect = a.num_labels <= gcap;
       unsigned long long *gt = hb.g_tab + hb.table_off[d.entry];
       const uint32_t staged_end = d.a0 + d.staged;
-      // each warp takes batches of 4 x 32 consecutive edges
-      for (uint32_t e0 = d.gbeg + wib * 128; e0 < d.gend; e0 += kWarps * 128) {
+      for (uint32_t e0 = d.gbeg + wib * 128; e0 < d.gend; e0 += kHubConsumerWarps * 128) {
         uint32_t k4[4];
         int32_t w4[4];
 #pragma unroll
@@ -810,7 +821,10 @@ __global__ void __launch_bounds__(kChunkThreads, 6) sweep_hub_aggregate(const Sw
         table64_add_batch<4>(gt, gcap - 1, gdirect, k4, w4);
       }
     }
-    __syncthreads(); // everybody is done with s_adj[stage] / s_item[stage]; s_item[stage ^ 1] is visible
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&s_empty[stage]); // this warp is done with the stage
+    }
   }
 }
 

@@ -34,7 +34,7 @@ def graphs(draw):
     return g
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(g=graphs(), seed=st.integers(0, 1000), mcw=st.integers(1, 40))
 def test_cluster_matches_oracle_on_random_multigraphs(g, seed, mcw):
     ctx = lp.create_default_context()
@@ -47,7 +47,7 @@ def test_cluster_matches_oracle_on_random_multigraphs(g, seed, mcw):
     assert (c < g.n).all() and H.cluster_weights_ok(g, c, mcw)
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(g=graphs(), seed=st.integers(0, 1000), k=st.integers(2, 9), slack=st.floats(0.0, 0.5))
 def test_refine_matches_oracle_on_random_multigraphs(g, seed, k, slack):
     rng = np.random.default_rng(seed)
