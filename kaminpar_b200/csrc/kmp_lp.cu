@@ -404,6 +404,7 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     hb.g_tab = h->hub_tab.p;
     hb.rank = h->rank;
     hb.world = h->world;
+    hb.queue = h->ctr32.p + 64 + s_idx; // zeroed with the other per-round counters
     if (hb.num_items > 0) {
       sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
     }
@@ -801,7 +802,7 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
 int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
   const uint32_t S = h->lists_S;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream)); // both proposal counters, moved
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
   h->mover_parity = 0;
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
     const SubRound q = subround_of_sg(h, sg);
@@ -1321,6 +1322,7 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream)); // hub work-queue cursors
   sa.sel_target = d_target.p;
   sa.sel_favored = mode == 0 ? d_fav.p : nullptr;
   sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
@@ -1523,7 +1525,7 @@ int kmp_lp_step_begin_iteration(kmp_lp_handle *h) {
   if (h == nullptr || h->step_mode < 0) {
     return fail(KMP_ERR_INVALID, "step_begin_* not called");
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 4 * sizeof(uint32_t), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream));
   h->mover_parity = 0;
   return KMP_OK;
 }

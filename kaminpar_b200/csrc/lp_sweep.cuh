@@ -625,6 +625,7 @@ struct HubArgs {
   Cand *__restrict__ part_best;           // per selection item
   Cand *__restrict__ part_fav;
   uint32_t rank, world;                   // hub entry i is owned by rank i % world
+  uint32_t *__restrict__ queue;           // work-queue cursor of this launch (zeroed per LP round)
 };
 constexpr uint32_t kSelPieceSlots = 8192;
 
@@ -711,13 +712,21 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
   if (wib == kHubConsumerWarps) {
     // ------------------------------- producer warp -------------------------------------------
     if (lane == 0) {
-      uint32_t k = 0;
-      for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, ++k) {
+      // items are claimed from a global cursor (dynamic load balancing: chunks of inactive hubs cost
+      // nothing, full chunks cost ~2048 gathers); valid = 2 tells the consumers to stop
+      for (uint32_t k = 0;; ++k) {
         const int stage = static_cast<int>(k % kHubStages);
         const uint32_t round = k / kHubStages;
         mbar_wait(&s_empty[stage], (round & 1u) ^ 1u); // passes immediately in the first round
+        const uint32_t it = atomicAdd(hb.queue, 1u);
         HubItem d{};
         d.valid = 0;
+        if (it >= hb.num_items) {
+          d.valid = 2;
+          s_item[stage] = d;
+          mbar_arrive(&s_full[stage]);
+          break;
+        }
         const uint32_t entry = hb.item_entry[it]; // the descriptor loads are independent
         const uint32_t u = hb.item_u[it];
         const uint32_t beg0 = hb.item_beg[it];
@@ -767,12 +776,14 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
   }
 
   // --------------------------------- consumer warps ----------------------------------------------
-  uint32_t k = 0;
-  for (uint32_t it = blockIdx.x; it < hb.num_items; it += gridDim.x, ++k) {
+  for (uint32_t k = 0;; ++k) {
     const int stage = static_cast<int>(k % kHubStages);
     const uint32_t round = k / kHubStages;
     mbar_wait(&s_full[stage], round & 1u);
     const HubItem d = s_item[stage];
+    if (d.valid == 2) {
+      break; // queue exhausted
+    }
     if (d.valid) {
       const uint32_t gcap = hub_cap(d.full_deg, a.num_labels);
       const bool gdirect = a.num_labels <= gcap;
