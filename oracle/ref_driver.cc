@@ -70,7 +70,20 @@ Graph make_graph(
 
 } // namespace
 
+#ifdef KMP_SHIM_PARALLEL
+#include <omp.h>
+#endif
+
 extern "C" {
+
+// number of OpenMP threads the parallel stand-in uses (no effect in the serial build)
+void kmpref_set_num_threads(int threads) {
+#ifdef KMP_SHIM_PARALLEL
+  omp_set_num_threads(threads > 0 ? threads : 1);
+#else
+  (void)threads;
+#endif
+}
 
 struct kmpref_lp_params {
   std::uint32_t num_iterations;        // 5
