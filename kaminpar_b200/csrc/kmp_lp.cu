@@ -150,9 +150,33 @@ struct kmp_lp_handle {
 namespace {
 
 // ---- small kernels --------------------------------------------------------------------------
-__global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32_t granule_log2, uint32_t base_sr,
-                            uint32_t large_degree_threshold, uint8_t *keys, uint32_t *vals, uint32_t *hist,
-                            uint32_t *max_deg) {
+// vertices per degree group of the schedule (hist[0..3]) among the visited ones
+__global__ void k_group_counts(uint32_t n, const uint32_t *xadj, uint32_t large_degree_threshold, uint32_t *hist) {
+  uint32_t c[4] = {0, 0, 0, 0};
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const uint32_t d = xadj[u + 1] - xadj[u];
+    if (d != 0 && d < large_degree_threshold) {
+      ++c[degree_group(d)];
+    }
+  }
+  for (int q = 0; q < 4; ++q) {
+    uint32_t v = c[q];
+    for (int o = 16; o > 0; o >>= 1) {
+      v += __shfl_xor_sync(kFull, v, o);
+    }
+    if ((threadIdx.x & 31) == 0 && v != 0) {
+      atomicAdd(&hist[q], v);
+    }
+  }
+}
+
+struct GroupSubrounds {
+  uint32_t s[4]; // hashed sub-rounds used by each degree group (<= S)
+};
+
+__global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, GroupSubrounds gs, uint32_t granule_log2,
+                            uint32_t base_sr, uint32_t large_degree_threshold, uint8_t *keys, uint32_t *vals,
+                            uint32_t *hist, uint32_t *max_deg) {
   uint32_t local_max = 0;
   for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     const uint32_t d = xadj[u + 1] - xadj[u];
@@ -161,7 +185,7 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, uint32
       key = kNumTiers * S; // never visited (label_propagation.h:1795, :1914-1915)
     } else {
       const uint32_t tier = d < kTier4MinDegree ? degree_group(d) : 4u;
-      key = tier * S + subround_of(u, granule_log2, base_sr, S);
+      key = tier * S + subround_of(u, granule_log2, base_sr, gs.s[degree_group(d)]);
     }
     keys[u] = static_cast<uint8_t>(key);
     vals[u] = u;
@@ -478,7 +502,21 @@ int ensure_lists(kmp_lp_handle *h) {
   KMP_CUDA(h->ctr32.ensure(512));
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
   const uint32_t base_sr = sync_base(h->cfg.seed, 0, 0, SALT_SUBROUND);
-  k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, h->cfg.sync_granule_log2, base_sr,
+  // Sub-rounds per degree group: S for a group holding >= 1/16 of the visited vertices, S/4 otherwise
+  // (a small group has few same-sub-round neighbours; its launches become 4x larger). DESIGN.md §3.
+  GroupSubrounds gs{};
+  {
+    k_group_counts<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, h->cfg.large_degree_threshold, h->ctr32.p);
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    KMP_CUDA(cudaMemcpyAsync(cnt, h->ctr32.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    KMP_CUDA(cudaStreamSynchronize(h->stream));
+    const uint64_t visited = static_cast<uint64_t>(cnt[0]) + cnt[1] + cnt[2] + cnt[3];
+    for (int q = 0; q < 4; ++q) {
+      gs.s[q] = (16ull * cnt[q] >= visited) ? S : std::max<uint32_t>(1, S / 4);
+    }
+    KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
+  }
+  k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, gs, h->cfg.sync_granule_log2, base_sr,
                                                         h->cfg.large_degree_threshold, h->sort_keys_in.p,
                                                         h->sort_vals_in.p, h->ctr32.p, h->ctr32.p + 300);
   KMP_CUDA(cudaGetLastError());
