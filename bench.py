@@ -363,9 +363,15 @@ def main():
     achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0
     all_bytes = 8 * edges + 16 * nodes
     sweep_ms_total = sum(g_ms)
+    traffic = None
+    try:  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/), if any
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f).get(wl, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "launches": g_launch[dom], "avg_launch_ms": g_ms[dom] / max(g_launch[dom], 1),
         "algorithmic_bytes_per_launch": alg_bytes / max(g_launch[dom], 1),
         "share_of_step": g_ms[dom] / tot_ms if tot_ms > 0 else None,
