@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("KMP_BENCH_WORKLOAD", "rmat22"))
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="clustering", choices=["clustering", "refinement"],
+                    help="refinement: one LabelPropagationRefiner.refine call on a hashed k-way partition (N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -260,7 +262,20 @@ def main():
 
         sharded = ShardedLP(CudaBackend(handle, dev), n, ctx.coarsening.clustering.lp.num_iterations, rank, world)
 
+    refine_handle = None
+    if args.mode == "refinement":
+        # SURVEY §8d refinement mode: hash-of-id blocks, max_block_weight = (1+eps)*ceil(n/k)
+        refine_handle = lp.LPHandle(lp._refine_config(ctx.refinement.lp, ctx.engine))
+        refine_handle.set_graph_device(n, m, d_xadj.data_ptr(), d_adj.data_ptr())
+        refine_handle.set_timing(True)
+        rng = np.random.default_rng(0)
+        part0 = rng.integers(0, k, n).astype(np.uint32)
+        mbw = ctx.partition.max_block_weights()
+
     def run_resident():
+        if refine_handle is not None:
+            refine_handle.upload_partition(part0)
+            return refine_handle.refine(k, mbw, None)[2]
         if sharded is None:
             return handle.cluster(mcw, fetch=False)[1]
         return sharded.compute_clustering(mcw, fetch=False)[2]
@@ -391,7 +406,7 @@ def main():
         "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": wl, "n": n, "m_directed": m, "k": k, "mode": "clustering",
+        "config": {"workload": wl, "n": n, "m_directed": m, "k": k, "mode": args.mode,
                    "max_cluster_weight": mcw, "iterations": last.iterations, "moved": last.moved_list(),
                    "num_clusters": last.num_clusters, "l2": "inputs_larger_than_l2" if m * 4 > 126e6 else "small_input",
                    "parallelism": "single" if world == 1 else f"frontier-sharded x{world} (replicated labels, NCCL all-gather of proposals)",
