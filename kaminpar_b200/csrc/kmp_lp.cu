@@ -144,6 +144,7 @@ struct kmp_lp_handle {
   int32_t step_mcw = 0;
   bool step_has_min = false, step_has_comm = false;
   uint32_t mover_parity = 0; // proposal counter in use: ctr32[0] (parity 0) or ctr32[3] (parity 1)
+  bool step_accumulated = false; // kmp_lp_step_commit already ran k_accumulate_movers for this sub-round
   bool stepping = false; // proposals are accumulated by kmp_lp_step_commit, not by the sweep kernels
 };
 
@@ -366,7 +367,16 @@ __global__ void k_unpack_movers(const uint32_t *gathered, uint32_t world, uint32
 // incoming[] / hist[] over the gathered proposals (the sweep kernels skip it when world > 1)
 template <int MODE>
 __global__ void k_accumulate_movers(const uint32_t *mv_u, const uint32_t *mv_t, const uint32_t *count,
-                                    const int32_t *vwgt, uint32_t base_commit, int32_t *incoming, int32_t *hist) {
+                                    const int32_t *vwgt, uint32_t base_commit, int32_t *incoming, int32_t *hist,
+                                    uint32_t k) {
+  extern __shared__ int32_t s_hist[];
+  const bool priv = (MODE == 1) && k * kLadderLevels <= kSmemPrivLimit;
+  if (priv) {
+    for (uint32_t b = threadIdx.x; b < k * kLadderLevels; b += blockDim.x) {
+      s_hist[b] = 0;
+    }
+    __syncthreads();
+  }
   const uint32_t cnt = *count;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
     const uint32_t u = mv_u[i];
@@ -374,7 +384,20 @@ __global__ void k_accumulate_movers(const uint32_t *mv_u, const uint32_t *mv_t, 
     if (MODE == 0) {
       atomicAdd(&incoming[mv_t[i]], w);
     } else {
-      atomicAdd(&hist[mv_t[i] * kLadderLevels + ladder_level(bijective32(u, base_commit))], w);
+      const uint32_t slot = mv_t[i] * kLadderLevels + ladder_level(bijective32(u, base_commit));
+      if (priv) {
+        atomicAdd(&s_hist[slot], w);
+      } else {
+        atomicAdd(&hist[slot], w);
+      }
+    }
+  }
+  if (priv) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < k * kLadderLevels; b += blockDim.x) {
+      if (s_hist[b] != 0) {
+        atomicAdd(&hist[b], s_hist[b]);
+      }
     }
   }
 }
@@ -400,7 +423,7 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
     sweep_thread<MODE, EW><<<grid_for(a.list_size, 256), 256, 0, h->stream>>>(a);
     break;
   case 1:
-    sweep_warp<MODE, EW><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->stream>>>(a);
+    sweep_warp<MODE, EW><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->stream>>>(a);
     break;
   case 2:
     sweep_warp_hash<MODE, EW>
@@ -777,7 +800,7 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   sa.base_tie = sync_base(h->cfg.seed, h->call_counter, iter, SALT_TIE);
   sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
   sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-  sa.accumulate = !h->stepping;
+  sa.accumulate = !h->stepping && rc.mode == 0; // refiner: accumulated by k_accumulate_movers (privatised)
   h->cur_subround = q.sr;
   sa.list = h->order.p + h->list_off[sg] + q.lo_a;
   sa.list_size = q.hi_a - q.lo_a;
@@ -803,11 +826,18 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
     h->kernel_launches += 3;
   } else {
     const uint32_t kgrid = grid_for(rc.num_labels, 128);
+    const size_t smem_k = rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0;
+    if (!h->step_accumulated) { // level histograms over all proposals (the stepping path did it already)
+      const size_t smem_h = rc.num_labels * kLadderLevels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * kLadderLevels * 4 : 0;
+      k_accumulate_movers<1><<<cgrid, 256, smem_h, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0),
+                                                               h->vwgt, ca.base_commit, h->incoming.p, h->hist.p, rc.num_labels);
+      ++h->kernel_launches;
+    }
     commit_begin<<<cgrid, 256, 0, h->stream>>>(h->acc.p, h->ctr32.p + (h->mover_parity ? 3 : 0));
     commit_refine_prepare<<<kgrid, 128, 0, h->stream>>>(ca);
     for (uint32_t p = 0; p < passes; ++p) {
       commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
-      commit_refine_decide<<<cgrid, 256, 0, h->stream>>>(ca);
+      commit_refine_decide<<<cgrid, 256, smem_k, h->stream>>>(ca);
     }
     h->kernel_launches += 3 + 2 * passes;
     if (rc.has_min) {
@@ -826,10 +856,10 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
   case 1: commit_apply_activate<0, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
   case 2: commit_apply_activate<0, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
   case 3: commit_apply_activate<0, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
+  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
   }
   h->kernel_launches += 1;
   h->mover_parity ^= 1u;
@@ -1605,14 +1635,18 @@ int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void 
   const uint32_t agrid = grid_for(q.size_a + q.size_b, 256, kSMs * 8);
   if (rc.mode == 0) {
     k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
-                                                          h->incoming.p, h->hist.p);
+                                                          h->incoming.p, h->hist.p, rc.num_labels);
   } else {
-    k_accumulate_movers<1><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
-                                                          h->incoming.p, h->hist.p);
+    const size_t smem_h = rc.num_labels * kLadderLevels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * kLadderLevels * 4 : 0;
+    k_accumulate_movers<1><<<agrid, 256, smem_h, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
+                                                               h->incoming.p, h->hist.p, rc.num_labels);
   }
   h->kernel_launches += 2;
   KMP_CUDA(cudaGetLastError());
-  return commit_subround(h, rc, iter, sg, q);
+  h->step_accumulated = true;
+  const int r2 = commit_subround(h, rc, iter, sg, q);
+  h->step_accumulated = false;
+  return r2;
 }
 
 int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved) {

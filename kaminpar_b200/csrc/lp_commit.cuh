@@ -129,7 +129,20 @@ __global__ void commit_refine_jmin(const CommitArgs a) {
   }
   a.jmin[b] = jm;
 }
+// Block-weight style accumulators are privatised per CTA in shared memory when k is small: millions of
+// proposals hitting k <= a few hundred global addresses serialise in the L2 atomic units (measured:
+// 783 us per launch for 0.7 M moves on k = 64 before, see profiles/README.md).
+constexpr uint32_t kSmemPrivLimit = 8192; // ints of dynamic shared memory a commit kernel may use
+
 __global__ void commit_refine_decide(const CommitArgs a) {
+  extern __shared__ int32_t s_acc[];
+  const bool priv = a.k <= kSmemPrivLimit;
+  if (priv) {
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      s_acc[b] = 0;
+    }
+    __syncthreads();
+  }
   const uint32_t cnt = *a.mover_count;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
     if (a.acc[i] != 0) {
@@ -140,7 +153,19 @@ __global__ void commit_refine_decide(const CommitArgs a) {
     const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
     if (static_cast<int>(lvl) >= a.jmin[t]) {
       a.acc[i] = 1;
-      atomicAdd(&a.out_delta[a.label[u]], node_weight(a, u));
+      if (priv) {
+        atomicAdd(&s_acc[a.label[u]], node_weight(a, u));
+      } else {
+        atomicAdd(&a.out_delta[a.label[u]], node_weight(a, u));
+      }
+    }
+  }
+  if (priv) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      if (s_acc[b] != 0) {
+        atomicAdd(&a.out_delta[b], s_acc[b]);
+      }
     }
   }
 }
@@ -203,6 +228,14 @@ __global__ void commit_refine_reset(const CommitArgs a) {
 // vertex as active (label_propagation.h:848-870). Rejected proposals stay active for the next
 // round. Thread 0 of the grid also zeroes the proposal counter of the NEXT sub-round.
 template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_apply_activate(const CommitArgs a) {
+  extern __shared__ int32_t s_delta[];
+  const bool priv = (MODE == 1) && a.k <= kSmemPrivLimit;
+  if (priv) {
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      s_delta[b] = 0;
+    }
+    __syncthreads();
+  }
   const uint32_t cnt = *a.mover_count;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t sub = tid % LANES;
@@ -230,8 +263,13 @@ template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_app
       if (acc == 1) {
         const int32_t w = node_weight(a, u);
         const uint32_t from = a.label[u];
-        atomicAdd(&a.weight[t], w);
-        atomicSub(&a.weight[from], w);
+        if (priv) {
+          atomicAdd(&s_delta[t], w);
+          atomicSub(&s_delta[from], w);
+        } else {
+          atomicAdd(&a.weight[t], w);
+          atomicSub(&a.weight[from], w);
+        }
         a.label[u] = t;
         ++moved;
       } else {
@@ -243,6 +281,14 @@ template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_app
       const uint32_t end = a.xadj[u + 1];
       for (uint32_t e = beg + sub; e < end; e += LANES) {
         a.active[a.adjncy[e]] = 1;
+      }
+    }
+  }
+  if (priv) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      if (s_delta[b] != 0) {
+        atomicAdd(&a.weight[b], s_delta[b]);
       }
     }
   }

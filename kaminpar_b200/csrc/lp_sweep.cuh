@@ -151,82 +151,121 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread
 // group 1: warp per vertex, deg <= 32, duplicates merged by match.any (no hash table)
 // ================================================================================================
 template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(const SweepArgs a) {
+  // V vertices per warp and loop iteration: all loads of a stage (vertex record; neighbour id; neighbour
+  // label) are issued for the V vertices before any of them is consumed, so a warp keeps V dependent
+  // load chains in flight instead of one.
+  constexpr int V = 4;
   unsigned long long edges = 0, nodes = 0;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = warp; i < a.list_size; i += nwarps) {
-    const uint32_t u = a.list[i];
-    if (a.active != nullptr) { // lane 0 reads, so that its later active[u] = 0 cannot split the warp
-      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
-      act = __shfl_sync(kFull, act, 0);
-      if (act == 0) {
-        continue;
+  for (uint32_t i0 = warp * V; i0 < a.list_size; i0 += nwarps * V) {
+    uint32_t u[V], beg[V], deg[V], own[V];
+    int32_t uw[V], own_w[V];
+    bool act[V], skip[V];
+    // stage 1: vertex records (lane q < V loads vertex q, then broadcast)
+    {
+      uint32_t lu = 0, lbeg = 0, ldeg = 0, lown = 0;
+      int32_t luw = 1, lown_w = 0;
+      int lact = 0;
+      if (lane < V && i0 + lane < a.list_size) {
+        lu = a.list[i0 + lane];
+        lact = a.active == nullptr ? 1 : static_cast<int>(a.active[lu]);
+        lbeg = a.xadj[lu];
+        ldeg = a.xadj[lu + 1] - lbeg;
+        lown = a.label[lu];
+        luw = a.vwgt != nullptr ? a.vwgt[lu] : 1;
+        lown_w = a.weight[lown];
       }
-    }
-    const uint32_t beg = a.xadj[u];
-    uint32_t deg = a.xadj[u + 1] - beg;
-    if (deg > a.max_num_neighbors) {
-      deg = a.max_num_neighbors;
-    }
-    const uint32_t own = a.label[u];
-    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
-    const int32_t own_w = a.weight[own];
-    if (lane == 0) {
-      edges += deg;
-      nodes += 1;
-      if (a.active != nullptr) {
-        a.active[u] = 0;
-      }
-    }
-    bool skip = false;
-    if (MODE == 1) {
-      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
-      skip = (own_w - uw) < mn;
-    }
-    uint32_t key = kEmpty;
-    int32_t w = 0;
-    if (!skip && static_cast<uint32_t>(lane) < deg) {
-      const uint32_t v = a.adjncy[beg + lane];
-      bool ok = true;
-      if (MODE == 1 && a.communities != nullptr) {
-        ok = a.communities[u] == a.communities[v];
-      }
-      if (ok) {
-        key = a.label[v];
-        w = EW ? a.adjwgt[beg + lane] : 1;
-      }
-    }
-    const unsigned peers = __match_any_sync(kFull, key);
-    int32_t rating;
-    if (EW) {
-      // sum of w over the lanes holding the same key (uniform 32-step loop: every lane takes part in
-      // every shuffle, so no partial-mask collectives are needed)
-      rating = 0;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int32_t wq = __shfl_sync(kFull, w, q);
-        rating += ((peers >> q) & 1u) ? wq : 0;
+      for (int q = 0; q < V; ++q) {
+        u[q] = __shfl_sync(kFull, lu, q);
+        act[q] = __shfl_sync(kFull, lact, q) != 0;
+        beg[q] = __shfl_sync(kFull, lbeg, q);
+        deg[q] = __shfl_sync(kFull, ldeg, q);
+        own[q] = __shfl_sync(kFull, lown, q);
+        uw[q] = __shfl_sync(kFull, luw, q);
+        own_w[q] = __shfl_sync(kFull, lown_w, q);
+        if (deg[q] > a.max_num_neighbors) {
+          deg[q] = a.max_num_neighbors;
+        }
+        skip[q] = false;
+        if (MODE == 1 && act[q]) {
+          const int32_t mn = a.min_w != nullptr ? a.min_w[own[q]] : 0;
+          skip[q] = (own_w[q] - uw[q]) < mn;
+        }
       }
-    } else {
-      rating = __popc(peers);
     }
-    const bool rep = (key != kEmpty) && (lane == __ffs(peers) - 1);
-    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
-    Cand c = cand_none(), f = cand_none();
-    if (rep) {
-      c = eval_candidate<MODE>(a, u, own, uw, own_w, key, rating, store_fav, f);
+    // stage 2: neighbour ids, stage 3: neighbour labels
+    uint32_t v[V], key[V];
+    int32_t w[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      v[q] = kEmpty;
+      w[q] = 0;
+      if (act[q] && !skip[q] && static_cast<uint32_t>(lane) < deg[q]) {
+        v[q] = a.adjncy[beg[q] + lane];
+        w[q] = EW ? a.adjwgt[beg[q] + lane] : 1;
+      }
     }
-    const Cand best = warp_argmax<MODE>(kFull, c);
-    Cand fav = cand_none();
-    if (MODE == 0 && store_fav) {
-      fav = warp_argmax<0>(kFull, f);
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      key[q] = kEmpty;
+      if (v[q] != kEmpty) {
+        bool ok = true;
+        if (MODE == 1 && a.communities != nullptr) {
+          ok = a.communities[u[q]] == a.communities[v[q]];
+        }
+        if (ok) {
+          key[q] = a.label[v[q]];
+        }
+      }
     }
-    if (lane == 0) {
-      uint32_t target;
-      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
-        const uint32_t idx = atomicAdd(a.mover_count, 1u);
-        emit_proposal<MODE>(a, idx, u, target, uw);
+    // stage 4: ratings by match.any, candidate weights gathered for all V vertices before evaluation
+    int32_t rating[V], kw[V];
+    bool rep[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      const unsigned peers = __match_any_sync(kFull, key[q]);
+      if (EW) {
+        rating[q] = 0;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int32_t wt = __shfl_sync(kFull, w[q], t);
+          rating[q] += ((peers >> t) & 1u) ? wt : 0;
+        }
+      } else {
+        rating[q] = __popc(peers);
+      }
+      rep[q] = (key[q] != kEmpty) && (lane == __ffs(peers) - 1);
+      kw[q] = rep[q] ? a.weight[key[q]] : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      if (!act[q]) {
+        continue; // warp-uniform
+      }
+      const bool store_fav = (MODE == 0) && (uw[q] == own_w[q]) && (own_w[q] <= a.max_cluster_weight / 2);
+      Cand c = cand_none(), f = cand_none();
+      if (rep[q]) {
+        c = eval_candidate_w<MODE>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], kw[q], store_fav, f);
+      }
+      const Cand best = warp_argmax<MODE>(kFull, c);
+      Cand fav = cand_none();
+      if (MODE == 0 && store_fav) {
+        fav = warp_argmax<0>(kFull, f);
+      }
+      if (lane == 0) {
+        edges += deg[q];
+        nodes += 1;
+        if (a.active != nullptr) {
+          a.active[u[q]] = 0;
+        }
+        uint32_t target;
+        if (finish_vertex<MODE>(a, u[q], own[q], store_fav, best, fav, target)) {
+          const uint32_t idx = atomicAdd(a.mover_count, 1u);
+          emit_proposal<MODE>(a, idx, u[q], target, uw[q]);
+        }
       }
     }
   }
