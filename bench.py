@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("KMP_BENCH_WORKLOAD", "rmat22"))
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm (e2e = null)")
     ap.add_argument("--mode", default="clustering", choices=["clustering", "refinement"],
                     help="refinement: one LabelPropagationRefiner.refine call on a hashed k-way partition (N=1 only)")
     args = ap.parse_args()
@@ -295,6 +296,7 @@ def main():
     g_edges = [0] * 5
     g_nodes = [0] * 5
     g_ms = [0.0] * 5
+    commit_ms = apply_ms = 0.0
     g_launch = [0] * 5
     last = None
     for _ in range(args.steps):
@@ -309,6 +311,8 @@ def main():
             g_nodes[q] += st.group_nodes[q]
             g_ms[q] += st.group_sweep_ms[q]
             g_launch[q] += st.group_launches[q]
+        commit_ms += st.group_sweep_ms[5]
+        apply_ms += st.group_sweep_ms[6]
         last = st
     barrier()
     clocks = sampler.stop()
@@ -334,7 +338,18 @@ def main():
 
         e2e_handle = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
 
+    refiner = p_graph_host = None
+    if args.mode == "refinement":
+        refiner = lp.LabelPropagationRefiner(ctx)
+        p_graph_host = lp.PartitionedGraph(g_host, k, part0)
+
     def e2e_step():
+        if refiner is not None:  # Refiner API: graph + partition H2D, refined partition + block weights D2H
+            p_graph_host.partition[:] = part0
+            refiner._graph = None
+            refiner.initialize(p_graph_host)
+            refiner.refine(p_graph_host, ctx.partition)
+            return refiner.last_stats.edges_scanned
         if world == 1:
             clusterer._graph = None  # new graph each step: forces the H2D copy, as one coarsening level does
             clusterer.compute_clustering(g_host, clustering=out_np)
@@ -344,16 +359,17 @@ def main():
         _, _, st_e = drv.compute_clustering(mcw, fetch=True)
         return st_e.edges_scanned
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
     e2e_edges = 0
-    for _ in range(args.steps):
-        e2e_edges += e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_edges += e2e_step()
+        torch.cuda.synchronize()
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     t = torch.tensor([e2e_s, float(e2e_edges)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -363,6 +379,9 @@ def main():
     e2e_value = e2e_edges / e2e_s
     h2d = (n + 1) * 4 + m * 4
     d2h = n * 4
+    if refiner is not None:
+        h2d += n * 4 + k * 4
+        d2h += k * 4
 
     if rank != 0:
         if world > 1:
@@ -394,6 +413,7 @@ def main():
                        "share_of_step": sweep_ms_total / tot_ms if tot_ms > 0 else None,
                        "per_group_ms": [x / args.steps for x in g_ms],
                        "per_group_edges": [x // args.steps for x in g_edges]},
+        "commit_ms": commit_ms / args.steps, "apply_activate_ms": apply_ms / args.steps,
     }
 
     cpu = None
@@ -412,8 +432,8 @@ def main():
                    "parallelism": "single" if world == 1 else f"frontier-sharded x{world} (replicated labels, NCCL all-gather of proposals)",
                    "subrounds": ctx.engine.sync_subrounds},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+        "e2e": None if args.no_e2e else {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d,
+                                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }

@@ -90,7 +90,8 @@ typedef struct {
   uint64_t group_edges[8];
   uint64_t group_nodes[8];
   uint64_t group_launches[8];
-  float group_sweep_ms[8];   /* only when timing is enabled */
+  float group_sweep_ms[8];   /* only when timing is enabled: [0..4] sweep tiers, [5] commit-rule kernels,
+                              * [6] apply + activate */
 } kmp_lp_stats;
 
 typedef struct kmp_lp_handle kmp_lp_handle;
@@ -173,6 +174,8 @@ int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_bl
                              const int32_t *min_block_weights, const uint32_t *communities,
                              const uint32_t *partition);
 int kmp_lp_step_begin_iteration(kmp_lp_handle *h);
+/* iter counts the LP rounds of this call from 0 and must stay below config.num_iterations (the commit of
+ * the last round does not maintain the active flags any more). */
 int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send);
 int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void *d_gathered);
 int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved);

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -48,6 +49,7 @@ int fail(int code, const std::string &msg) {
 constexpr int kNumGroups = 4; // degree groups of the schedule
 constexpr int kNumTiers = 5;  // kernel tiers: group 3 is split at degree 2048
 constexpr int kSMs = 148;
+constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512)
 
 template <typename T> struct DevBuf {
   T *p = nullptr;
@@ -123,8 +125,17 @@ struct kmp_lp_handle {
   DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk, t4_sel_entry, t4_sel_piece, t4_sel_begin;
   DevBuf<uint32_t> t4_item_u, t4_item_beg, t4_item_deg; // static per item: vertex, xadj[u], degree
   std::vector<uint32_t> t4_item_off, t4_sel_off; // S + 1
+  // A sub-round's hubs are processed in waves whose table regions together stay below
+  // hub_wave_slots, so that the table traffic of a wave stays in L2; every wave reuses the same memory.
+  struct HubWave {
+    uint32_t item_lo, item_hi, sel_lo, sel_hi; // absolute ranges in the t4_item_* / t4_sel_* arrays
+  };
+  std::vector<HubWave> t4_waves;
+  std::vector<uint32_t> t4_wave_off; // S + 1
+  uint64_t hub_wave_slots = 1ull << 28; // 2 GiB of packed entries (KMP_HUB_WAVE_SLOTS overrides, for experiments)
   DevBuf<Cand> t4_part_best, t4_part_fav;
   uint64_t t4_max_slots = 0;
+  uint32_t hub_cap_pct = 300; // tier-4 table slots per 100 labels (KMP_HUB_CAP_PCT overrides, for experiments)
   DevBuf<unsigned long long> hub_tab; // packed (key << 32 | rating) entries, kEmpty64 when unused
   uint32_t mover_cap = 0;
   uint32_t cur_subround = 0;
@@ -441,33 +452,62 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
   default: {
     HubArgs hb{};
     const uint32_t s_idx = h->cur_subround;
-    hb.item_entry = h->t4_item_entry.p + h->t4_item_off[s_idx];
-    hb.item_chunk = h->t4_item_chunk.p + h->t4_item_off[s_idx];
-    hb.item_u = h->t4_item_u.p + h->t4_item_off[s_idx];
-    hb.item_beg = h->t4_item_beg.p + h->t4_item_off[s_idx];
-    hb.item_deg = h->t4_item_deg.p + h->t4_item_off[s_idx];
-    hb.num_items = h->t4_item_off[s_idx + 1] - h->t4_item_off[s_idx];
     hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
     hb.g_tab = h->hub_tab.p;
+    hb.cap_pct = h->hub_cap_pct;
     hb.rank = h->rank;
     hb.world = h->world;
-    hb.queue = h->ctr32.p + 64 + s_idx; // zeroed with the other per-round counters
-    if (hb.num_items > 0) {
-      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
-    }
-    hb.sel_entry = h->t4_sel_entry.p + h->t4_sel_off[s_idx];
-    hb.sel_piece = h->t4_sel_piece.p + h->t4_sel_off[s_idx];
-    hb.num_sel_items = h->t4_sel_off[s_idx + 1] - h->t4_sel_off[s_idx];
     hb.sel_begin = h->t4_sel_begin.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
+    // one aggregate + partial-select pair per wave; all waves share the table memory (kept clean by the select)
+    for (uint32_t w = h->t4_wave_off[s_idx]; w < h->t4_wave_off[s_idx + 1]; ++w) {
+      const kmp_lp_handle::HubWave &wv = h->t4_waves[w];
+      hb.item_entry = h->t4_item_entry.p + wv.item_lo;
+      hb.item_chunk = h->t4_item_chunk.p + wv.item_lo;
+      hb.item_u = h->t4_item_u.p + wv.item_lo;
+      hb.item_beg = h->t4_item_beg.p + wv.item_lo;
+      hb.item_deg = h->t4_item_deg.p + wv.item_lo;
+      hb.num_items = wv.item_hi - wv.item_lo;
+      hb.queue = h->ctr32.p + 64 + w; // zeroed with the other per-round counters
+      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
+      hb.sel_entry = h->t4_sel_entry.p + wv.sel_lo;
+      hb.sel_piece = h->t4_sel_piece.p + wv.sel_lo;
+      hb.num_sel_items = wv.sel_hi - wv.sel_lo;
+      hb.part_best = h->t4_part_best.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
+      hb.part_fav = h->t4_part_fav.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
+      sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->stream>>>(a, hb);
+      h->kernel_launches += 2;
+    }
     hb.part_best = h->t4_part_best.p;
     hb.part_fav = h->t4_part_fav.p;
-    sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->stream>>>(a, hb);
     sweep_hub_final<MODE><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->stream>>>(a, hb);
-    h->kernel_launches += 2;
     break;
   }
   }
   return cudaGetLastError();
+}
+
+// timing mode: bracket a section of the stream with an event pair tagged with a stats slot
+// (0..4 sweep tiers, 5 commit-rule kernels, 6 apply + activate)
+int timed_begin(kmp_lp_handle *h, int tag) {
+  if (!h->timing) {
+    return -1;
+  }
+  if (h->sweep_events_used == h->sweep_events.size()) {
+    cudaEvent_t x, y;
+    cudaEventCreate(&x);
+    cudaEventCreate(&y);
+    h->sweep_events.emplace_back(x, y);
+    h->sweep_event_group.push_back(0);
+  }
+  const int idx = static_cast<int>(h->sweep_events_used++);
+  h->sweep_event_group[idx] = tag;
+  cudaEventRecord(h->sweep_events[idx].first, h->stream);
+  return idx;
+}
+void timed_end(kmp_lp_handle *h, int idx) {
+  if (idx >= 0) {
+    cudaEventRecord(h->sweep_events[idx].second, h->stream);
+  }
 }
 
 cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs &a_in) {
@@ -476,21 +516,7 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs 
   }
   SweepArgs a = a_in;
   a.counters = h->ctr64.p + group;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (h->timing) {
-    if (h->sweep_events_used == h->sweep_events.size()) {
-      cudaEvent_t x, y;
-      cudaEventCreate(&x);
-      cudaEventCreate(&y);
-      h->sweep_events.emplace_back(x, y);
-      h->sweep_event_group.push_back(0);
-    }
-    h->sweep_event_group[h->sweep_events_used] = group;
-    e0 = h->sweep_events[h->sweep_events_used].first;
-    e1 = h->sweep_events[h->sweep_events_used].second;
-    ++h->sweep_events_used;
-    cudaEventRecord(e0, h->stream);
-  }
+  const int ev = timed_begin(h, group);
   const bool ew = h->adjwgt != nullptr;
   cudaError_t e;
   if (mode == 0) {
@@ -498,9 +524,7 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs 
   } else {
     e = ew ? launch_sweep_t<1, true>(h, group, a) : launch_sweep_t<1, false>(h, group, a);
   }
-  if (h->timing) {
-    cudaEventRecord(e1, h->stream);
-  }
+  timed_end(h, ev);
   ++h->kernel_launches;
   ++h->sweep_launches;
   ++h->group_launches[group];
@@ -574,6 +598,8 @@ int ensure_lists(kmp_lp_handle *h) {
     const uint32_t t4_begin = h->list_off[4 * S], t4_end = h->list_off[5 * S];
     const uint32_t t4_cnt = t4_end - t4_begin;
     h->t4_item_off.assign(S + 1, 0);
+    h->t4_wave_off.assign(S + 1, 0);
+    h->t4_waves.clear();
     h->t4_max_slots = 0;
     if (t4_cnt > 0) {
       DevBuf<uint32_t> d_deg, d_beg, d_ids;
@@ -588,6 +614,15 @@ int ensure_lists(kmp_lp_handle *h) {
       std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), sbeg(t4_cnt), ient, ichk, sent, spiece;
       h->t4_sel_off.assign(S + 1, 0);
       size_t max_sel = 0;
+      // at most kMaxHubWaves work-queue cursors exist per LP round: coarsen the waves if necessary
+      uint64_t wave_slots = h->hub_wave_slots;
+      {
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < t4_cnt; ++i) {
+          total += hub_cap(deg[i], 0xFFFFFFFFu, h->hub_cap_pct);
+        }
+        wave_slots = std::max<uint64_t>(wave_slots, total / (kMaxHubWaves / 2 - S) + 1);
+      }
       KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       KMP_CUDA(cudaStreamSynchronize(h->stream));
       d_deg.release();
@@ -596,13 +631,25 @@ int ensure_lists(kmp_lp_handle *h) {
       for (uint32_t sr = 0; sr < S; ++sr) {
         const uint32_t lo = h->list_off[4 * S + sr] - t4_begin, hi = h->list_off[4 * S + sr + 1] - t4_begin;
         uint64_t slots = 0;
-        for (uint32_t i = lo; i < hi; ++i) {
-          uint64_t cap = 32;
-          while (cap < 2ull * deg[i]) {
-            cap <<= 1;
+        kmp_lp_handle::HubWave wave{static_cast<uint32_t>(ient.size()), 0, static_cast<uint32_t>(sent.size()), 0};
+        auto close_wave = [&]() {
+          wave.item_hi = static_cast<uint32_t>(ient.size());
+          wave.sel_hi = static_cast<uint32_t>(sent.size());
+          if (wave.item_hi > wave.item_lo) {
+            h->t4_waves.push_back(wave);
           }
-          if (slots + cap > 0xFFFFFFFFull) {
-            return fail(KMP_ERR_UNSUPPORTED, "high-degree table of one sub-round exceeds 2^32 slots");
+          wave.item_lo = wave.item_hi;
+          wave.sel_lo = wave.sel_hi;
+          h->t4_max_slots = std::max(h->t4_max_slots, slots);
+          slots = 0;
+        };
+        for (uint32_t i = lo; i < hi; ++i) {
+          const uint64_t cap = hub_cap(deg[i], 0xFFFFFFFFu, h->hub_cap_pct);
+          if (static_cast<uint64_t>(deg[i]) * h->hub_cap_pct / 100 + 1 > 0xFFFFFFFFull) {
+            return fail(KMP_ERR_UNSUPPORTED, "high-degree table of one vertex exceeds 2^32 slots");
+          }
+          if (slots > 0 && slots + cap > wave_slots) {
+            close_wave();
           }
           toff[i] = static_cast<uint32_t>(slots);
           slots += cap;
@@ -621,9 +668,10 @@ int ensure_lists(kmp_lp_handle *h) {
             spiece.push_back(c);
           }
         }
+        close_wave();
+        h->t4_wave_off[sr + 1] = static_cast<uint32_t>(h->t4_waves.size());
         h->t4_sel_off[sr + 1] = static_cast<uint32_t>(sent.size());
         max_sel = std::max<size_t>(max_sel, sent.size() - h->t4_sel_off[sr]);
-        h->t4_max_slots = std::max(h->t4_max_slots, slots);
         h->t4_item_off[sr + 1] = static_cast<uint32_t>(ient.size());
       }
       KMP_CUDA(h->t4_table_off.ensure(t4_cnt));
@@ -817,9 +865,12 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
 int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
   CommitArgs ca = make_commit_args(h, rc);
   ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  // the flags set in the last round of a call are never read (every call starts with all vertices active)
+  ca.activate = h->cfg.num_iterations == 0 || iter + 1 < h->cfg.num_iterations;
   const uint32_t size = q.size_a + q.size_b;
   const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
   const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
+  int ev = timed_begin(h, 5);
   if (rc.mode == 0) {
     commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
     commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
@@ -849,18 +900,21 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
     commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
     h->kernel_launches += 2;
   }
+  timed_end(h, ev);
+  ev = timed_begin(h, 6);
   // apply + activate in one launch; it also zeroes the other proposal counter for the next sub-round
   const int variant = (rc.mode == 0 ? 0 : 4) + (q.group > 3 ? 3 : q.group);
   switch (variant) {
-  case 0: commit_apply_activate<0, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 1: commit_apply_activate<0, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 2: commit_apply_activate<0, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 3: commit_apply_activate<0, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, 0, h->stream>>>(ca); break;
-  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 8), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  case 0: commit_apply_activate<0, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 1: commit_apply_activate<0, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 2: commit_apply_activate<0, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 3: commit_apply_activate<0, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
   }
+  timed_end(h, ev);
   h->kernel_launches += 1;
   h->mover_parity ^= 1u;
   KMP_CUDA(cudaGetLastError());
@@ -870,7 +924,7 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
 int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
   const uint32_t S = h->lists_S;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
   h->mover_parity = 0;
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
     const SubRound q = subround_of_sg(h, sg);
@@ -932,7 +986,9 @@ int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
     for (size_t i = 0; i < h->sweep_events_used; ++i) {
       float t = 0.f;
       cudaEventElapsedTime(&t, h->sweep_events[i].first, h->sweep_events[i].second);
-      sweep += t;
+      if (h->sweep_event_group[i] < kNumTiers) {
+        sweep += t;
+      }
       stats->group_sweep_ms[h->sweep_event_group[i]] += t;
     }
     stats->sweep_ms = sweep;
@@ -1066,6 +1122,12 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_ALLOC, "out of host memory");
   }
   h->cfg = *cfg;
+  if (const char *e = std::getenv("KMP_HUB_CAP_PCT")) { // experiment knobs; results do not depend on them
+    h->hub_cap_pct = std::max(110, std::atoi(e));
+  }
+  if (const char *e = std::getenv("KMP_HUB_WAVE_SLOTS")) {
+    h->hub_wave_slots = static_cast<uint64_t>(std::max(32ll, std::atoll(e)));
+  }
   if (h->cfg.sync_subrounds == 0) {
     h->cfg.sync_subrounds = 8;
   }
@@ -1390,7 +1452,7 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream)); // hub work-queue cursors
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // hub work-queue cursors
   sa.sel_target = d_target.p;
   sa.sel_favored = mode == 0 ? d_fav.p : nullptr;
   sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
@@ -1593,7 +1655,7 @@ int kmp_lp_step_begin_iteration(kmp_lp_handle *h) {
   if (h == nullptr || h->step_mode < 0) {
     return fail(KMP_ERR_INVALID, "step_begin_* not called");
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 128 * sizeof(uint32_t), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
   h->mover_parity = 0;
   return KMP_OK;
 }

@@ -298,41 +298,44 @@ __device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_
 // ratings are one 64-bit atomicAdd on the same entry (ratings are non-negative int32 sums).
 constexpr unsigned long long kEmpty64 = 0xFFFFFFFF00000000ull;
 
-// B independent inserts: the first probe of all B keys is issued before any result is consumed.
+// B independent inserts: the first probe of all B keys is a plain L2 load (ld.cg), issued for the whole
+// batch before any result is consumed. A key that is already present then costs one fire-and-forget
+// RED; an empty slot is claimed with one CAS that also deposits the rating.
 template <int B>
-__device__ __forceinline__ void table64_add_batch(unsigned long long *tab, uint32_t mask, bool direct,
+__device__ __forceinline__ void table64_add_batch(unsigned long long *tab, uint32_t cap, bool direct,
                                                   const uint32_t (&k)[B], const int32_t (&w)[B]) {
   uint32_t slot[B];
   unsigned long long prev[B];
 #pragma unroll
   for (int j = 0; j < B; ++j) {
-    slot[j] = direct ? k[j] : (lowbias32(k[j]) & mask);
+    slot[j] = direct ? k[j] : __umulhi(lowbias32(k[j]), cap); // cap need not be a power of two
     prev[j] = kEmpty64;
     if (k[j] != kEmpty) {
-      prev[j] = atomicCAS(&tab[slot[j]], kEmpty64,
-                          (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]));
+      prev[j] = __ldcg(&tab[slot[j]]);
     }
   }
 #pragma unroll
   for (int j = 0; j < B; ++j) {
-    if (k[j] != kEmpty && prev[j] != kEmpty64) {
-      if (static_cast<uint32_t>(prev[j] >> 32) == k[j]) {
-        atomicAdd(&tab[slot[j]], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
-      } else {
-        uint32_t sl = (slot[j] + 1) & mask;
-        while (true) {
-          const unsigned long long pv =
-              atomicCAS(&tab[sl], kEmpty64, (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]));
-          if (pv == kEmpty64) {
-            break;
-          }
-          if (static_cast<uint32_t>(pv >> 32) == k[j]) {
-            atomicAdd(&tab[sl], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
-            break;
-          }
-          sl = (sl + 1) & mask;
-        }
+    if (k[j] == kEmpty) {
+      continue;
+    }
+    const unsigned long long mine = (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]);
+    uint32_t sl = slot[j];
+    unsigned long long pv = prev[j];
+    while (true) {
+      if (static_cast<uint32_t>(pv >> 32) == k[j]) {
+        atomicAdd(&tab[sl], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
+        break;
       }
+      if (pv == kEmpty64) { // the slot looked empty: claim it
+        pv = atomicCAS(&tab[sl], kEmpty64, mine);
+        if (pv == kEmpty64) {
+          break;
+        }
+        continue; // somebody else claimed it first: re-examine the same slot
+      }
+      sl = sl + 1 == cap ? 0 : sl + 1;
+      pv = __ldcg(&tab[sl]);
     }
   }
 }
@@ -664,14 +667,17 @@ struct HubArgs {
   Cand *__restrict__ part_best;           // per selection item
   Cand *__restrict__ part_fav;
   uint32_t rank, world;                   // hub entry i is owned by rank i % world
+  uint32_t cap_pct;                       // table slots per 100 distinct labels (hub_cap)
   uint32_t *__restrict__ queue;           // work-queue cursor of this launch (zeroed per LP round)
 };
 constexpr uint32_t kSelPieceSlots = 8192;
 
-__device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_labels) {
+// slots of a hub's table region: pct/100 x the number of labels it can meet (not a power of two: the
+// region is written and scanned in full every sub-round, so its size is DRAM traffic)
+__host__ __device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_labels, uint32_t pct) {
   const uint32_t distinct = full_degree < num_labels ? full_degree : num_labels;
-  const uint32_t cap = pow2_ceil(2 * distinct);
-  return cap < 32 ? 32 : cap;
+  const unsigned long long cap = static_cast<unsigned long long>(distinct) * pct / 100 + 1;
+  return cap < 32 ? 32u : static_cast<uint32_t>(cap);
 }
 
 // ---- 1-D bulk TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------
@@ -824,7 +830,7 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
       break; // queue exhausted
     }
     if (d.valid) {
-      const uint32_t gcap = hub_cap(d.full_deg, a.num_labels);
+      const uint32_t gcap = hub_cap(d.full_deg, a.num_labels, hb.cap_pct);
       const bool gdirect = a.num_labels <= gcap;
       unsigned long long *gt = hb.g_tab + hb.table_off[d.entry];
       const uint32_t staged_end = d.a0 + d.staged;
@@ -868,7 +874,7 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
           }
           w4[j] = r;
         }
-        table64_add_batch<4>(gt, gcap - 1, gdirect, k4, w4);
+        table64_add_batch<4>(gt, gcap, gdirect, k4, w4);
       }
     }
     __syncwarp();
@@ -895,7 +901,7 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_p
       const uint32_t own = a.label[u];
       const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
       const int32_t own_w = a.weight[own];
-      const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+      const uint32_t gcap = hub_cap(full_deg, a.num_labels, hb.cap_pct);
       const uint32_t lo = hb.sel_piece[it] * kSelPieceSlots;
       const uint32_t hi = lo + kSelPieceSlots < gcap ? lo + kSelPieceSlots : gcap;
       unsigned long long *gt = hb.g_tab + hb.table_off[entry];
@@ -982,7 +988,7 @@ template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const
     const uint32_t own = a.label[u];
     const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
     const int32_t own_w = a.weight[own];
-    const uint32_t gcap = hub_cap(full_deg, a.num_labels);
+    const uint32_t gcap = hub_cap(full_deg, a.num_labels, hb.cap_pct);
     const uint32_t pieces = (gcap + kSelPieceSlots - 1) / kSelPieceSlots;
     const uint32_t first = hb.sel_begin[i];
     const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);

@@ -130,6 +130,21 @@ def test_t1_clustering_matches_oracle_sync(name, seed):
     assert np.array_equal(c2, expect2)
 
 
+@pytest.mark.parametrize("name", ["rmat15_sorted", "star_hub", "rmat14_unsorted_w"])
+@pytest.mark.parametrize("knobs", [("150", "6000"), ("300", "40000")])
+def test_t1_hub_table_layout_does_not_change_results(name, knobs, monkeypatch):
+    """The tier-4 table sizing and the wave budget are performance knobs (read once per handle): tight
+    tables and one-hub waves must give the oracle's clustering as well."""
+    monkeypatch.setenv("KMP_HUB_CAP_PCT", knobs[0])
+    monkeypatch.setenv("KMP_HUB_WAVE_SLOTS", knobs[1])
+    g = get_graph(name)
+    ctx, mcw = ctx_for(g, 8, seed=3)
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    c = clusterer.compute_clustering(g)
+    assert np.array_equal(c, B.oracle_lp_cluster(g, 3, mcw, schedule=B.SYNC))
+
+
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("k", [2, 4, 64])
 def test_t1_refinement_matches_oracle_sync(name, k):
