@@ -178,6 +178,106 @@ def cpu_reference_run(name, steps, warmup):
     return edges / dt, dt, kind, cores, desc
 
 
+def cpu_contraction_run(name, steps, warmup):
+    """contract_clustering of the unmodified reference (oracle/_ref; OpenMP stand-in when it is there) or the
+    numpy port, on a bounded sample. Returns (fine_edges_per_s, s_per_step, kind, cores, description)."""
+    from kaminpar_b200.graph import CSRGraph
+    from oracle import bindings as B
+    from oracle import contraction_oracle as CO
+
+    sample = CPU_SAMPLE.get(name, name)
+    xadj, adj, k = generate(sample, "cpu")
+    g = CSRGraph(xadj.numpy().astype(np.uint32), adj.numpy().astype(np.uint32), sorted=True)
+    cl = B.oracle_lp_cluster(g, 0, B.oracle_max_cluster_weight(g, k), schedule=B.SYNC)
+    cores = 1
+    if B.have_reference():
+        kind, fn = "reference", (lambda: B.ref_contract(g, cl, 1))
+    else:
+        kind, fn = "port", (lambda: CO.contract(g.xadj, g.adjncy, None, None, cl))
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    desc = f"{sample}: n={g.n} m={g.m}, contract_clustering (UNBUFFERED) of the LP clustering on {cores} thread(s)"
+    return g.m / dt, dt, kind, cores, desc
+
+
+def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
+    """--mode contraction: a step = one contract_clustering of the (device-resident) LP clustering."""
+    import torch
+
+    from kaminpar_b200 import contraction as KC
+    from kaminpar_b200 import lp
+
+    metric, unit = "contraction_fine_edges_per_second", "edges/s"
+    handle.set_timing(False)
+    handle.cluster(mcw, fetch=False)
+    cl_host = handle.download_labels()
+    for _ in range(args.warmup):
+        KC.contract_on_handle(handle, None).close()
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    sampler.start()
+    tot_ms, launches, last = 0.0, 0, None
+    for _ in range(args.steps):
+        cg = KC.contract_on_handle(handle, None)
+        tot_ms += cg.stats.device_ms
+        launches += cg.stats.kernel_launches
+        last = (cg.stats.c_n, cg.stats.c_m, cg.stats.cut_edges, cg.stats.sort_bits)
+        cg.close()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    value = m * args.steps / (tot_ms * 1e-3)
+    c_n, c_m, cut, bits = last
+    # e2e: graph + clustering from host memory, coarse graph + mapping back to the host
+    ctx = lp.create_default_context()
+    ctx.engine.device = local_rank
+    e2e = None
+    if not args.no_e2e:
+        h2 = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
+
+        def e2e_step():
+            h2.set_graph(g_host)
+            cg = KC.contract_on_handle(h2, cl_host)
+            cg.get()
+            cg.mapping()
+            cg.close()
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": m * args.steps / e2e_s, "unit": unit, "h2d_bytes_per_step": (n + 1) * 4 + m * 4 + n * 4,
+               "d2h_bytes_per_step": (c_n + 1) * 4 + c_m * 8 + c_n * 4 + n * 4, "ms_per_step": e2e_s / args.steps * 1e3}
+    peak, peak_src = peaks()
+    alg = 8 * m + 12 * n + 12 * c_m + 8 * c_n
+    achieved = alg * args.steps / (tot_ms * 1e-3) / 1e9
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "n": n, "m_directed": m, "k": k, "mode": "contraction",
+                   "coarse_n": c_n, "coarse_m": c_m, "inter_cluster_edges": cut, "sort_bits": bits,
+                   "l2": "inputs_larger_than_l2" if m * 4 > 126e6 else "small_input"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "contract_clustering (key pass + radix sort + reduce-by-key)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                     "note": "8 B per fine edge + 12 B per fine vertex + 12 B per coarse edge + 8 B per coarse vertex; "
+                             "the radix passes over the inter-cluster edges are not algorithmic bytes"},
+    }
+    if not args.no_cpu_baseline:
+        eps, dt, kind, cores, desc = cpu_contraction_run(args.workload, args.cpu_steps, 1)
+        line["cpu_baseline"] = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,8 +288,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm (e2e = null)")
-    ap.add_argument("--mode", default="clustering", choices=["clustering", "refinement"],
-                    help="refinement: one LabelPropagationRefiner.refine call on a hashed k-way partition (N=1 only)")
+    ap.add_argument("--mode", default="clustering", choices=["clustering", "refinement", "contraction"],
+                    help="refinement: one LabelPropagationRefiner.refine call on a hashed k-way partition (N=1 only); "
+                         "contraction: contract_clustering of the LP clustering (SURVEY §8f-1, N=1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -255,6 +356,8 @@ def main():
     handle = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
     handle.set_graph_device(n, m, d_xadj.data_ptr(), d_adj.data_ptr())
     handle.set_timing(True)
+    if args.mode == "contraction":
+        return contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank)
     sharded = None
     if world > 1:
         # strong scaling: ONE graph, vertex frontier sharded over the ranks, proposals all-gathered

@@ -10,17 +10,20 @@
 //   class Refiner    kaminpar-shm/refinement/refiner.h:18-57
 //   LPClustering     kaminpar-shm/coarsening/clustering/lp_clusterer.h:19 / lp_clusterer.cc:376-399
 //   LabelPropagationRefiner  kaminpar-shm/refinement/lp/lp_refiner.h:19 / lp_refiner.cc:357-376
+//   CoarseGraph / contract_clustering  kaminpar-shm/coarsening/contraction/cluster_contraction.h:22-56
 //
 // Error convention: the reference's path has no error codes (KASSERT aborts); here a non-zero
 // status of the C ABI becomes std::runtime_error. There is no CPU fallback.
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <span>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "kaminpar_b200_contraction.h"
 #include "kaminpar_b200_lp.h"
 
 namespace kaminpar_b200 {
@@ -139,6 +142,7 @@ public:
     }
   }
   [[nodiscard]] const kmp_lp_stats &last_stats() const { return _stats; }
+  [[nodiscard]] kmp_lp_handle *handle() const { return _handle.get(); } // graph holder for contract_clustering
 
 private:
   static kmp_lp_config make_config(const LabelPropagationCoarseningContext &c, const EngineContext &e) {
@@ -211,5 +215,66 @@ private:
   std::span<const NodeID> _communities;
   kmp_lp_stats _stats{};
 };
+
+// Same surface as kaminpar::shm::CoarseGraph (cluster_contraction.h:22-32). The coarse graph lives on the
+// device; get() copies it into host vectors once (a maintainer's glue wraps them into a CSRGraph).
+class CoarseGraph {
+public:
+  struct HostCSR {
+    std::vector<EdgeID> nodes;
+    std::vector<NodeID> edges;
+    std::vector<NodeWeight> node_weights;
+    std::vector<EdgeWeight> edge_weights;
+  };
+  explicit CoarseGraph(kmp_coarse_graph *g, const kmp_contraction_stats &stats) : _g(g), _stats(stats) {}
+  CoarseGraph(const CoarseGraph &) = delete;
+  CoarseGraph &operator=(const CoarseGraph &) = delete;
+  ~CoarseGraph() { kmp_coarse_destroy(_g); }
+
+  [[nodiscard]] NodeID n() const { return kmp_coarse_n(_g); }
+  [[nodiscard]] EdgeID m() const { return kmp_coarse_m(_g); }
+  const HostCSR &get() {
+    if (_host.nodes.empty()) {
+      _host.nodes.resize(static_cast<std::size_t>(n()) + 1);
+      _host.edges.resize(m());
+      _host.node_weights.resize(n());
+      _host.edge_weights.resize(m());
+      detail::check(kmp_coarse_download(_g, _host.nodes.data(), _host.edges.data(), _host.node_weights.data(),
+                                        _host.edge_weights.data(), nullptr));
+    }
+    return _host;
+  }
+  // fine[u] = coarse[mapping[u]] (cluster_contraction_preprocessing.h:36-40)
+  void project_up(std::span<const BlockID> coarse, std::span<BlockID> fine) const {
+    if (coarse.size() != n() || fine.size() != kmp_coarse_fine_n(_g)) {
+      throw std::invalid_argument("project_up: wrong span size");
+    }
+    detail::check(kmp_coarse_project_up(_g, coarse.data(), fine.data()));
+  }
+  // coarse[mapping[u]] = fine[u] (:42-46)
+  void project_down(std::span<const BlockID> fine, std::span<BlockID> coarse) const {
+    if (coarse.size() != n() || fine.size() != kmp_coarse_fine_n(_g)) {
+      throw std::invalid_argument("project_down: wrong span size");
+    }
+    detail::check(kmp_coarse_project_down(_g, fine.data(), coarse.data()));
+  }
+  [[nodiscard]] const kmp_contraction_stats &stats() const { return _stats; }
+  [[nodiscard]] const kmp_coarse_graph *device() const { return _g; } // kmp_coarse_device_arrays for the next level
+
+private:
+  kmp_coarse_graph *_g;
+  kmp_contraction_stats _stats;
+  HostCSR _host;
+};
+
+// contract_clustering(graph, clustering, con_ctx) (cluster_contraction.h:47-50). `clusterer` is the LP
+// clusterer that already holds `graph` on the device (no second H2D copy); an empty `clustering` span
+// contracts by the clustering its last compute_clustering() left on the device.
+inline std::unique_ptr<CoarseGraph> contract_clustering(kmp_lp_handle *graph_holder, std::span<const NodeID> clustering) {
+  kmp_coarse_graph *g = nullptr;
+  kmp_contraction_stats stats{};
+  detail::check(kmp_contract_clustering(graph_holder, clustering.empty() ? nullptr : clustering.data(), &g, &stats));
+  return std::make_unique<CoarseGraph>(g, stats);
+}
 
 } // namespace kaminpar_b200

@@ -21,6 +21,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include "../../include/kaminpar_b200_contraction.h"
 #include "../../include/kaminpar_b200_lp.h"
 #include "lp_commit.cuh"
 #include "lp_device.cuh"
@@ -1777,3 +1778,5 @@ int kmp_lp_step_finish(kmp_lp_handle *h, uint32_t *labels_out, int32_t *block_we
 }
 
 } // extern "C"
+
+#include "kmp_contract.cuh"

@@ -166,6 +166,26 @@ def ref_max_block_weights(g, k, eps=0.03) -> np.ndarray:
     return out
 
 
+def ref_contract(g, clustering, algorithm=1):
+    """The unmodified reference's contract_clustering (0 BUFFERED, 1 UNBUFFERED = default preset,
+    2 UNBUFFERED_NAIVE). Returns the raw (non-canonical) result dict."""
+    cl = np.ascontiguousarray(clustering, np.uint32)
+    c_xadj = np.zeros(g.n + 1, np.uint32)
+    c_adj = np.zeros(max(g.m, 1), np.uint32)
+    c_vw = np.zeros(max(g.n, 1), np.int32)
+    c_ew = np.zeros(max(g.m, 1), np.int32)
+    mapping = np.zeros(max(g.n, 1), np.uint32)
+    c_m = C.c_uint32(0)
+    lib = ref()
+    lib.kmpref_contract.restype = C.c_uint32
+    c_n = int(lib.kmpref_contract(
+        *_garrs(g), cl.ctypes.data_as(C.c_void_p), C.c_int(algorithm), c_xadj.ctypes.data_as(C.c_void_p),
+        c_adj.ctypes.data_as(C.c_void_p), c_vw.ctypes.data_as(C.c_void_p), c_ew.ctypes.data_as(C.c_void_p),
+        mapping.ctypes.data_as(C.c_void_p), C.byref(c_m)))
+    return dict(c_n=c_n, c_xadj=c_xadj[: c_n + 1].copy(), c_adjncy=c_adj[: c_m.value].copy(), c_vwgt=c_vw[:c_n].copy(),
+                c_adjwgt=c_ew[: c_m.value].copy(), mapping=mapping[: g.n].copy())
+
+
 # ------------------------------------------------------------------------------------------------
 # Oracle restatement (oracle/lp_oracle.cc)
 # ------------------------------------------------------------------------------------------------

@@ -8,12 +8,15 @@
 //   Random::reseed -> [rearrange_by_degree_buckets -> remove_isolated_nodes]
 //   -> LPClustering(ctx.coarsening).compute_clustering(...)
 //   -> LabelPropagationRefiner(ctx).initialize/refine(p_graph, p_ctx)
+// and, for the contraction row, contract_clustering(graph, clustering, con_ctx)
+// (coarsening/contraction/cluster_contraction.h:47-56, driven like basic_cluster_coarsener.cc:27-45).
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <vector>
 
 #include "kaminpar-shm/coarsening/clustering/lp_clusterer.h"
+#include "kaminpar-shm/coarsening/contraction/cluster_contraction.h"
 #include "kaminpar-shm/coarsening/max_cluster_weights.h"
 #include "kaminpar-shm/datastructures/csr_graph.h"
 #include "kaminpar-shm/datastructures/graph.h"
@@ -306,6 +309,50 @@ void kmpref_max_block_weights(
   for (std::uint32_t b = 0; b < k; ++b) {
     out[b] = ctx.partition.max_block_weight(b);
   }
+}
+
+// contract_clustering(graph, clustering, con_ctx) (cluster_contraction.cc:22-50). algorithm: 0 BUFFERED,
+// 1 UNBUFFERED (default preset, presets.cc:181-183), 2 UNBUFFERED_NAIVE. Outputs are caller-allocated
+// upper bounds: c_xadj[n+1], c_adjncy[m], c_vwgt[n], c_adjwgt[m], mapping[n] (fine -> coarse, via
+// CoarseGraph::project_up of the identity). Returns c_n; *c_m_out = directed coarse edges.
+std::uint32_t kmpref_contract(
+    std::uint32_t n, std::uint32_t m, const std::uint32_t *xadj, const std::uint32_t *adjncy,
+    const std::int32_t *vwgt, const std::int32_t *adjwgt, const std::uint32_t *clustering, int algorithm,
+    std::uint32_t *c_xadj, std::uint32_t *c_adjncy, std::int32_t *c_vwgt, std::int32_t *c_adjwgt,
+    std::uint32_t *mapping, std::uint32_t *c_m_out
+) {
+  Graph graph = make_graph(n, m, xadj, adjncy, vwgt, adjwgt, false);
+  Context ctx = create_default_context();
+  ContractionCoarseningContext con_ctx = ctx.coarsening.contraction;
+  con_ctx.algorithm = algorithm == 0   ? ContractionAlgorithm::BUFFERED
+                      : algorithm == 1 ? ContractionAlgorithm::UNBUFFERED
+                                       : ContractionAlgorithm::UNBUFFERED_NAIVE;
+  StaticArray<NodeID> cl = copy_array<NodeID>(clustering, n);
+  std::unique_ptr<CoarseGraph> coarse = contract_clustering(graph, std::move(cl), con_ctx);
+  const CSRGraph &cg = coarse->get().csr_graph();
+  const std::uint32_t c_n = cg.n();
+  const std::uint32_t c_m = cg.m();
+  for (std::uint32_t u = 0; u <= c_n; ++u) {
+    c_xadj[u] = cg.raw_nodes()[u];
+  }
+  for (std::uint32_t u = 0; u < c_n; ++u) {
+    c_vwgt[u] = cg.node_weight(u);
+  }
+  for (std::uint32_t e = 0; e < c_m; ++e) {
+    c_adjncy[e] = cg.raw_edges()[e];
+    c_adjwgt[e] = cg.edge_weight(e);
+  }
+  std::vector<BlockID> ident(c_n);
+  for (std::uint32_t u = 0; u < c_n; ++u) {
+    ident[u] = u;
+  }
+  std::vector<BlockID> fine(n);
+  coarse->project_up(ident, fine);
+  for (std::uint32_t u = 0; u < n; ++u) {
+    mapping[u] = fine[u];
+  }
+  *c_m_out = c_m;
+  return c_n;
 }
 
 } // extern "C"

@@ -31,6 +31,16 @@ int main() {
     for (NodeID c : clustering) {
       if (c >= g.n()) return 2;
     }
+    // contraction by the clustering that is still on the device, then projections
+    auto coarse = contract_clustering(clusterer.handle(), {});
+    NodeWeight total = 0;
+    for (NodeWeight w : coarse->get().node_weights) total += w;
+    if (total != static_cast<NodeWeight>(g.n()) || coarse->get().nodes.size() != coarse->n() + 1u) return 5;
+    std::vector<BlockID> cpart(coarse->n()), fine(g.n()), back(coarse->n());
+    for (NodeID c = 0; c < coarse->n(); ++c) cpart[c] = c % 3;
+    coarse->project_up(cpart, fine);
+    coarse->project_down(fine, back);
+    if (back != cpart) return 6;
     std::vector<BlockID> part(g.n());
     for (NodeID u = 0; u < g.n(); ++u) part[u] = u % 2;
     std::vector<BlockWeight> bw(2), maxw{9, 9};
