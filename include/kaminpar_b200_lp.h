@@ -174,8 +174,7 @@ int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_bl
                              const int32_t *min_block_weights, const uint32_t *communities,
                              const uint32_t *partition);
 int kmp_lp_step_begin_iteration(kmp_lp_handle *h);
-/* iter counts the LP rounds of this call from 0 and must stay below config.num_iterations (the commit of
- * the last round does not maintain the active flags any more). */
+/* iter counts the LP rounds of this call from 0 */
 int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send);
 int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void *d_gathered);
 int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved);

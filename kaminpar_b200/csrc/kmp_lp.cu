@@ -866,8 +866,6 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
 int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
   CommitArgs ca = make_commit_args(h, rc);
   ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-  // the flags set in the last round of a call are never read (every call starts with all vertices active)
-  ca.activate = h->cfg.num_iterations == 0 || iter + 1 < h->cfg.num_iterations;
   const uint32_t size = q.size_a + q.size_b;
   const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
   const uint32_t cgrid = grid_for(size, 256, kSMs * 8);

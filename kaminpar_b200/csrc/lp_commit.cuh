@@ -32,7 +32,6 @@ struct CommitArgs {
   const uint32_t *__restrict__ mover_count;
   uint32_t *__restrict__ next_mover_count; // zeroed for the following sub-round
   uint32_t base_commit;
-  bool activate; // false in the last LP round of a call: nobody reads the active flags afterwards
   // clusterer
   int32_t *__restrict__ incoming; // [n]
   uint32_t *__restrict__ slotmap; // [n], kEmpty when unused
@@ -310,11 +309,11 @@ template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_app
     const uint8_t acc1 = has1 ? a.acc[i1] : static_cast<uint8_t>(0);
     // level 2: adjacency ranges (all lanes); slot owner, old label and weight (lane 0)
     uint32_t beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
-    if (acc0 == 1 && a.activate) {
+    if (acc0 == 1) {
       beg0 = a.xadj[u0];
       end0 = a.xadj[u0 + 1];
     }
-    if (acc1 == 1 && a.activate) {
+    if (acc1 == 1) {
       beg1 = a.xadj[u1];
       end1 = a.xadj[u1 + 1];
     }
