@@ -274,7 +274,7 @@ def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
     if not args.no_cpu_baseline:
         eps, dt, kind, cores, desc = cpu_contraction_run(args.workload, args.cpu_steps, 1)
         line["cpu_baseline"] = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -311,8 +311,9 @@ def main():
             "config": {"workload": args.workload, "k": k, "mode": "clustering", "sample": CPU_SAMPLE.get(args.workload)},
             "cpu_baseline": {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": eps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
-        return 0
+        }), flush=True)
+        # two OpenMP runtimes live in this process (torch's and the stand-in's): skip interpreter teardown
+        os._exit(0)
 
     import torch
     import torch.distributed as dist
@@ -542,7 +543,7 @@ def main():
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -77,8 +77,18 @@ __device__ __forceinline__ uint32_t owner_of_edge(const uint32_t *x, uint32_t lo
   return lo;
 }
 
+// tile_lo[t] = owner of the first edge of tile t (t < tiles); tile_lo[tiles] = owner of the last edge.
+// One thread per tile, so that the CTAs of the key pass do not start with a serial 2 x log2(n) search.
+__global__ void k_tile_owners(uint32_t n, uint32_t m, const uint32_t *xadj, uint32_t tiles, uint32_t *tile_lo) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= tiles; t += gridDim.x * blockDim.x) {
+    const uint32_t e = t < tiles ? t * kTileEdges : m - 1;
+    tile_lo[t] = owner_of_edge(xadj, 0, n, e);
+  }
+}
+
 template <bool EW>
 __global__ void __launch_bounds__(256) k_contract_edge_keys(uint32_t n, uint32_t m, const uint32_t *__restrict__ xadj,
+                                                            const uint32_t *__restrict__ tile_lo,
                                                             const uint32_t *__restrict__ adjncy,
                                                             const int32_t *__restrict__ adjwgt,
                                                             const uint32_t *__restrict__ mapping, uint32_t shift,
@@ -87,16 +97,11 @@ __global__ void __launch_bounds__(256) k_contract_edge_keys(uint32_t n, uint32_t
   using BlockScan = cub::BlockScan<uint32_t, 256>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
   __shared__ uint32_t s_x[kTileVerts + 1];
-  __shared__ uint32_t s_lo, s_hi;
   __shared__ unsigned long long s_base;
   const uint32_t e0 = blockIdx.x * kTileEdges;
   const uint32_t e1 = e0 + kTileEdges < m ? e0 + kTileEdges : m; // e0 < m by the grid size
-  if (threadIdx.x == 0) {
-    s_lo = owner_of_edge(xadj, 0, n, e0);
-    s_hi = owner_of_edge(xadj, 0, n, e1 - 1);
-  }
-  __syncthreads();
-  const uint32_t u_lo = s_lo, u_hi = s_hi;
+  // the owners of this tile's edges lie in [u_lo, u_hi] (u_hi: owner of the next tile's first edge)
+  const uint32_t u_lo = tile_lo[blockIdx.x], u_hi = tile_lo[blockIdx.x + 1];
   const bool staged = u_hi - u_lo + 1 <= kTileVerts;
   if (staged) {
     for (uint32_t i = threadIdx.x; i <= u_hi - u_lo; i += blockDim.x) {
@@ -208,7 +213,8 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
     KMP_CUDA(cudaStreamSynchronize(st));
     return KMP_OK;
   }
-  ScratchBuf<uint32_t> d_cl, flags, rank;
+  // scratch lives in the handle (grow-only): no cudaMalloc / cudaFree on the timed path after the first call
+  DevBuf<uint32_t> &d_cl = h->ct_cl, &flags = h->ct_flags, &rank = h->ct_rank;
   const uint32_t *cl = nullptr;
   if (clustering != nullptr) {
     KMP_CUDA(d_cl.ensure(n));
@@ -244,28 +250,28 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   KMP_CUDA(cudaMemsetAsync(cg->vwgt.p, 0, static_cast<size_t>(c_n) * 4, st));
   k_map_and_weigh<<<grid_for(n, 256), 256, 0, st>>>(n, cl, rank.p, h->vwgt, cg->mapping.p, cg->vwgt.p);
   launches += 4;
-  flags.release();
-  rank.release();
   // ---- 2. edge keys ----------------------------------------------------------------------------
   const uint32_t shift = std::max<uint32_t>(1, ceil_log2_u32(c_n));
   const uint32_t bits = shift + std::max<uint32_t>(1, ceil_log2_u32(c_n));
   unsigned long long cut = 0;
-  ScratchBuf<unsigned long long> keys_a, keys_b, counter;
-  ScratchBuf<int32_t> vals_a, vals_b;
+  DevBuf<unsigned long long> &keys_a = h->pairs_a, &keys_b = h->pairs_b, &counter = h->ct_counter;
+  DevBuf<int32_t> &vals_a = h->ct_vals_a, &vals_b = h->ct_vals_b;
   KMP_CUDA(counter.ensure(2));
   KMP_CUDA(cudaMemsetAsync(counter.p, 0, 16, st));
   if (m > 0) {
     KMP_CUDA(keys_a.ensure(m));
     KMP_CUDA(vals_a.ensure(m));
     const uint32_t tiles = (m + kTileEdges - 1) / kTileEdges;
+    KMP_CUDA(flags.ensure(static_cast<size_t>(tiles) + 1)); // the leader flags are dead: reuse as tile_lo
+    k_tile_owners<<<grid_for(static_cast<uint64_t>(tiles) + 1, 256), 256, 0, st>>>(n, m, h->xadj, tiles, flags.p);
     if (h->adjwgt != nullptr) {
-      k_contract_edge_keys<true><<<tiles, 256, 0, st>>>(n, m, h->xadj, h->adjncy, h->adjwgt, cg->mapping.p, shift,
-                                                        keys_a.p, vals_a.p, counter.p);
+      k_contract_edge_keys<true><<<tiles, 256, 0, st>>>(n, m, h->xadj, flags.p, h->adjncy, h->adjwgt, cg->mapping.p,
+                                                        shift, keys_a.p, vals_a.p, counter.p);
     } else {
-      k_contract_edge_keys<false><<<tiles, 256, 0, st>>>(n, m, h->xadj, h->adjncy, nullptr, cg->mapping.p, shift,
-                                                         keys_a.p, vals_a.p, counter.p);
+      k_contract_edge_keys<false><<<tiles, 256, 0, st>>>(n, m, h->xadj, flags.p, h->adjncy, nullptr, cg->mapping.p,
+                                                         shift, keys_a.p, vals_a.p, counter.p);
     }
-    ++launches;
+    launches += 2;
     KMP_CUDA(cudaGetLastError());
     KMP_CUDA(cudaMemcpyAsync(&cut, counter.p, 8, cudaMemcpyDeviceToHost, st));
     KMP_CUDA(cudaStreamSynchronize(st));

@@ -143,7 +143,11 @@ struct kmp_lp_handle {
   DevBuf<uint8_t> sort_keys_in, sort_keys_out;
   DevBuf<uint32_t> sort_vals_in;
   DevBuf<unsigned char> cub_tmp;
-  DevBuf<unsigned long long> pairs_a, pairs_b;
+  DevBuf<unsigned long long> pairs_a, pairs_b; // two-hop sort; contraction: edge keys (double buffer)
+  // contraction scratch (kmp_contract.cuh), grow-only like the rest
+  DevBuf<int32_t> ct_vals_a, ct_vals_b;
+  DevBuf<uint32_t> ct_flags, ct_rank, ct_cl;
+  DevBuf<unsigned long long> ct_counter;
   bool slot_state_clean = false; // incoming/slotmap/chist zeroed for current n
 
   uint32_t call_counter = 0;
@@ -1507,6 +1511,12 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->cub_tmp.release();
   h->pairs_a.release();
   h->pairs_b.release();
+  h->ct_vals_a.release();
+  h->ct_vals_b.release();
+  h->ct_flags.release();
+  h->ct_rank.release();
+  h->ct_cl.release();
+  h->ct_counter.release();
   h->slot_state_clean = false;
   return KMP_OK;
 }
