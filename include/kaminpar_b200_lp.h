@@ -102,6 +102,10 @@ const char *kmp_last_error(void);
 /* Fill cfg with the default-preset values for the clusterer (mode 0) or refiner (mode 1). */
 void kmp_lp_default_config(int mode, kmp_lp_config *cfg);
 
+/* Environment knobs read once per handle in kmp_lp_create (experiments / tests only; results never
+ * depend on them): KMP_HUB_CAP_PCT = slots of a high-degree vertex's table region per 100 labels
+ * (default 300), KMP_HUB_WAVE_SLOTS = 8-byte table slots one wave of high-degree vertices may use
+ * (default 2^28 = 2 GiB; smaller values process a sub-round's hubs in more waves). */
 int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out);
 int kmp_lp_destroy(kmp_lp_handle *h);
 

@@ -111,3 +111,23 @@ def test_properties():
 def test_empty_graph():
     o = CO.contract(np.zeros(1, np.uint32), np.zeros(0, np.uint32), None, None, np.zeros(0, np.uint32))
     assert o["c_n"] == 0 and len(o["c_xadj"]) == 1
+
+
+@pytest.mark.skipif(not B.have_reference(), reason="oracle/_ref not built (authoring container only)")
+def test_oracle_matches_live_reference_random_multigraphs():
+    """Random small graphs with parallel edges, self-loops and weights, random clusterings: the oracle ==
+    the unmodified reference (default algorithm) after canonicalisation."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.integers(0, 120), st.integers(0, 2**31 - 1))
+    def run(n, m_und, seed):
+        rng = np.random.default_rng(seed)
+        edges = [(int(a), int(b)) for a, b in rng.integers(0, n, (m_und, 2))]
+        g = H.from_edges(n, edges, vwgt=rng.integers(1, 5, n), ew=rng.integers(1, 6, m_und).tolist())
+        cl = rng.integers(0, n, n).astype(np.uint32)
+        r = B.ref_contract(g, cl, 1)
+        assert CO.equal(oracle_of(g, cl), CO.canonicalize(**r, clustering=cl))
+
+    run()
