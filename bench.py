@@ -130,78 +130,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(name, steps, warmup):
-    """The reference's own CPU path (oracle/_ref: unmodified sources, serial oneTBB stand-in => one
-    core) or, if that library did not travel, the oracle port of the same algorithm. Returns
-    (edges_per_s, seconds_per_step, kind, cores, sample_description)."""
-    import torch
-
-    from kaminpar_b200.graph import CSRGraph
-    from oracle import bindings as B
+def _cpu_worker(name, mode, steps, warmup):
+    """Run oracle/cpu_baseline_worker.py on a bounded sample of workload `name` in a child process that
+    never loads torch (isolation: see the worker's header). Returns
+    (units_per_s, s_per_step, kind, cores, description)."""
+    import subprocess
+    import tempfile
 
     sample = CPU_SAMPLE.get(name, name)
     xadj, adj, k = generate(sample, "cpu")
-    g = CSRGraph(xadj.numpy().astype(np.uint32), adj.numpy().astype(np.uint32), sorted=True)
-    mcw = B.oracle_max_cluster_weight(g, k)
-    # scanned-edge count of the sequential schedule (deterministic for a seed)
-    _, st = B.oracle_lp_cluster(g, 0, mcw, schedule=B.SEQ, return_stats=True)
-    edges = int(st[0].edges_scanned)
-    cores = 1
-    if B.have_parallel_reference():  # unmodified reference sources on the host cores (OpenMP TBB stand-in)
-        kind, fn = "reference", (lambda: B.ref_lp_cluster(g, 0, mcw, parallel=True))
-        # use the thread count that is fastest for the reference on this box (all cores is not always
-        # best: the graph is first-touched by one thread), so that the baseline is not handicapped
-        avail = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
-        best = None
-        for t in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 16)}, reverse=True):
-            B.ref_omp().kmpref_set_num_threads(t)
-            fn()
-            t0 = time.perf_counter()
-            fn()
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, t)
-        cores = best[1]
-        B.ref_omp().kmpref_set_num_threads(cores)
-    elif B.have_reference():
-        kind, fn = "reference", (lambda: B.ref_lp_cluster(g, 0, mcw))
-    else:
-        kind, fn = "port", (lambda: B.oracle_lp_cluster(g, 0, mcw, schedule=B.SEQ))
-    for _ in range(warmup):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fn()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    desc = (f"{sample}: n={g.n} m={g.m} k={k}, LPClustering.compute_clustering on {cores} thread(s) "
-            f"({edges} scanned edges/step counted by the 1-thread schedule)")
-    return edges / dt, dt, kind, cores, desc
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sample.npz")
+        np.savez(path, xadj=xadj.numpy().astype(np.uint32), adjncy=adj.numpy().astype(np.uint32), k=np.array([k]))
+        del xadj, adj
+        last_err = ""
+        for extra in ([], ["serial"]):  # second try: the serial stand-in (1 core), should the OpenMP one fail
+            r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline_worker", path, mode, str(steps), str(warmup)]
+                               + extra, cwd=ROOT, capture_output=True, text=True,
+                               env=dict(os.environ, OMP_STACKSIZE=os.environ.get("OMP_STACKSIZE", "64M")))
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                d = json.loads(lines[-1])
+                return d["value"], d["seconds_per_step"], d["kind"], d["cores"], f"{sample}: {d['desc']}"
+            last_err = f"rc={r.returncode} {r.stderr[-300:]}"
+    raise RuntimeError("CPU baseline worker failed: " + last_err)
+
+
+def cpu_reference_run(name, steps, warmup):
+    """The reference's own CPU path (oracle/_ref: unmodified sources on the host cores through the OpenMP
+    stand-in for oneTBB; serial stand-in or the oracle port if that did not travel), bounded sample."""
+    return _cpu_worker(name, "lp", steps, warmup)
 
 
 def cpu_contraction_run(name, steps, warmup):
-    """contract_clustering of the unmodified reference (oracle/_ref; OpenMP stand-in when it is there) or the
-    numpy port, on a bounded sample. Returns (fine_edges_per_s, s_per_step, kind, cores, description)."""
-    from kaminpar_b200.graph import CSRGraph
-    from oracle import bindings as B
-    from oracle import contraction_oracle as CO
-
-    sample = CPU_SAMPLE.get(name, name)
-    xadj, adj, k = generate(sample, "cpu")
-    g = CSRGraph(xadj.numpy().astype(np.uint32), adj.numpy().astype(np.uint32), sorted=True)
-    cl = B.oracle_lp_cluster(g, 0, B.oracle_max_cluster_weight(g, k), schedule=B.SYNC)
-    cores = 1
-    if B.have_reference():
-        kind, fn = "reference", (lambda: B.ref_contract(g, cl, 1))
-    else:
-        kind, fn = "port", (lambda: CO.contract(g.xadj, g.adjncy, None, None, cl))
-    for _ in range(warmup):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        fn()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    desc = f"{sample}: n={g.n} m={g.m}, contract_clustering (UNBUFFERED) of the LP clustering on {cores} thread(s)"
-    return g.m / dt, dt, kind, cores, desc
+    """contract_clustering of the unmodified reference (oracle/_ref) or the numpy port, bounded sample."""
+    return _cpu_worker(name, "contraction", steps, warmup)
 
 
 def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):

@@ -13,6 +13,10 @@ from typing import Optional
 
 import numpy as np
 
+# precaution for the OpenMP stand-in build of the reference (sizeable per-thread buffers on the stack);
+# has to be in the environment before libgomp initialises
+os.environ.setdefault("OMP_STACKSIZE", "64M")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref.so")          # serial stand-in: deterministic, pins the oracle
 REF_OMP_LIB = os.path.join(_HERE, "_ref", "libkaminpar_ref_omp.so")  # OpenMP stand-in: all host cores (CPU baseline)

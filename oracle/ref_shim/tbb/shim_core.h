@@ -33,6 +33,8 @@
 #include <mutex>
 #include <type_traits>
 #include <utility>
+#include <array>
+#include <cstdlib>
 #include <vector>
 
 namespace tbb {
@@ -324,8 +326,19 @@ public:
   enumerable_thread_specific(A0 &&a0, A1 &&a1, Args &&...args)
       : _init([=] { return std::make_unique<T>(a0, a1, args...); }) {}
 
-  enumerable_thread_specific(enumerable_thread_specific &&) noexcept = default;
-  enumerable_thread_specific &operator=(enumerable_thread_specific &&) noexcept = default;
+  enumerable_thread_specific(enumerable_thread_specific &&o) noexcept
+      : _init(std::move(o._init)), _slots(std::move(o._slots)), _by_thread(o._by_thread) {
+    o._by_thread.fill(nullptr);
+  }
+  enumerable_thread_specific &operator=(enumerable_thread_specific &&o) noexcept {
+    if (this != &o) {
+      _init = std::move(o._init);
+      _slots = std::move(o._slots);
+      _by_thread = o._by_thread;
+      o._by_thread.fill(nullptr);
+    }
+    return *this;
+  }
   enumerable_thread_specific(const enumerable_thread_specific &o) : _init(o._init) {  // slots copied, thread map rebuilt lazily
     for (const auto &p : o._slots) {
       if constexpr (std::is_copy_constructible_v<T>) {
@@ -343,14 +356,11 @@ public:
 
   reference local() {
 #ifdef KMP_SHIM_PARALLEL
+    // the slot table has a fixed size and exists from construction on: every thread of a team calls
+    // local() at the same moment when a parallel loop starts, and a lazily (re)allocated table raced
     const int t = shim_detail::thread_index();
-    if (_by_thread.empty()) {
-#pragma omp critical(kmp_shim_ets)
-      {
-        if (_by_thread.empty()) {
-          _by_thread.assign(static_cast<std::size_t>(shim_detail::num_threads()) + 1, nullptr);
-        }
-      }
+    if (static_cast<std::size_t>(t) >= kMaxSlots) {
+      std::abort();
     }
     T *p = _by_thread[static_cast<std::size_t>(t)];
     if (p == nullptr) {
@@ -371,7 +381,7 @@ public:
   reference local(bool &exists) {
 #ifdef KMP_SHIM_PARALLEL
     const int t = shim_detail::thread_index();
-    exists = !_by_thread.empty() && _by_thread[static_cast<std::size_t>(t)] != nullptr;
+    exists = static_cast<std::size_t>(t) < kMaxSlots && _by_thread[static_cast<std::size_t>(t)] != nullptr;
 #else
     exists = !_slots.empty();
 #endif
@@ -382,7 +392,7 @@ public:
   bool empty() const { return _slots.empty(); }
   void clear() {
     _slots.clear();
-    _by_thread.clear();
+    _by_thread.fill(nullptr);
   }
 
   it_type begin() { return it_type(_slots.begin()); }
@@ -412,7 +422,8 @@ public:
 private:
   std::function<std::unique_ptr<T>()> _init;
   std::vector<std::unique_ptr<T>> _slots;
-  std::vector<T *> _by_thread; // parallel mode: slot of each OpenMP thread
+  static constexpr std::size_t kMaxSlots = 1024;
+  std::array<T *, kMaxSlots> _by_thread{}; // parallel mode: slot of each OpenMP thread (never reallocated)
 };
 
 // ---- combinable -----------------------------------------------------------------------------
