@@ -13,8 +13,10 @@
 //   3. one pass over the m fine edges: key = (mapping[u] << b | mapping[v]), value = w(u,v); edges inside
 //      a cluster are dropped at the source (block-level compaction, one atomic per 2048 edges). The source
 //      vertex of an edge is found by a binary search in the tile's slice of xadj staged in shared memory.
-//   4. LSD radix sort of the surviving (key, value) pairs over exactly 2·ceil(log2 c_n) key bits
-//   5. reduce-by-key -> unique coarse edges with summed weights; c_xadj by binary search per coarse vertex
+//   4. LSD radix sort of the surviving (key, value) pairs over exactly 2·ceil(log2 c_n) key bits; with unit
+//      edge weights (the finest level) the keys alone are sorted
+//   5. reduce-by-key (run-length encode when unweighted) -> unique coarse edges with summed weights;
+//      c_xadj by binary search per coarse vertex
 // Steps 4-5 use CUB (library sort / segmented reduce, like cuBLAS for a plain GEMM); 1-3 and the
 // CSR assembly are hand-written. Everything is HBM-streaming integer work: algorithmic bytes per fine
 // edge = 4 (adjncy) + 4 (mapping gather) [+ 4 weight] read, and per surviving edge 12 B written, then
@@ -23,12 +25,40 @@
 
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_reduce.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+
+// Output arrays come from the device's stream-ordered memory pool (cudaMallocAsync): a coarsening
+// loop allocates and frees coarse graphs of hundreds of MB per level, and cudaMalloc / cudaFree of that
+// size cost milliseconds and serialise the device. The pool keeps freed blocks (release threshold set
+// in contract_impl), so after the first level an allocation is a pointer bump.
+template <typename T> struct PoolBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t alloc(size_t n, cudaStream_t st) {
+    release();
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&p), std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e == cudaSuccess) {
+      cap = std::max<size_t>(n, 1);
+    } else {
+      p = nullptr;
+    }
+    return e;
+  }
+  // all work on the buffer has completed when this is called (contract_impl synchronises its stream)
+  void release() {
+    if (p != nullptr) {
+      cudaFreeAsync(p, nullptr);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+};
 
 struct kmp_coarse_graph {
   int device = 0;
   uint32_t fine_n = 0, c_n = 0, c_m = 0;
-  DevBuf<uint32_t> xadj, adjncy, mapping;
-  DevBuf<int32_t> vwgt, adjwgt;
+  PoolBuf<uint32_t> xadj, adjncy, mapping;
+  PoolBuf<int32_t> vwgt, adjwgt;
 };
 
 namespace {
@@ -152,7 +182,9 @@ __global__ void __launch_bounds__(256) k_contract_edge_keys(uint32_t n, uint32_t
   for (int j = 0; j < 8; ++j) {
     if (key[j] != ~0ull) {
       keys[o] = key[j];
-      vals[o] = val[j];
+      if (EW) {
+        vals[o] = val[j];
+      }
       ++o;
     }
   }
@@ -206,9 +238,15 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   uint32_t launches = 0;
   cg->device = h->device;
   cg->fine_n = n;
-  KMP_CUDA(cg->mapping.ensure(n));
-  KMP_CUDA(cg->xadj.ensure(1));
+  {
+    cudaMemPool_t pool = nullptr;
+    KMP_CUDA(cudaDeviceGetDefaultMemPool(&pool, h->device));
+    unsigned long long keep = ~0ull; // freed blocks stay in the pool (kmp_lp_free_scratch trims it)
+    KMP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  KMP_CUDA(cg->mapping.alloc(n, st));
   if (n == 0) {
+    KMP_CUDA(cg->xadj.alloc(1, st));
     KMP_CUDA(cudaMemsetAsync(cg->xadj.p, 0, sizeof(uint32_t), st));
     KMP_CUDA(cudaStreamSynchronize(st));
     return KMP_OK;
@@ -246,7 +284,7 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   }
   const uint32_t c_n = host2[0];
   cg->c_n = c_n;
-  KMP_CUDA(cg->vwgt.ensure(c_n));
+  KMP_CUDA(cg->vwgt.alloc(c_n, st));
   KMP_CUDA(cudaMemsetAsync(cg->vwgt.p, 0, static_cast<size_t>(c_n) * 4, st));
   k_map_and_weigh<<<grid_for(n, 256), 256, 0, st>>>(n, cl, rank.p, h->vwgt, cg->mapping.p, cg->vwgt.p);
   launches += 4;
@@ -260,7 +298,9 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   KMP_CUDA(cudaMemsetAsync(counter.p, 0, 16, st));
   if (m > 0) {
     KMP_CUDA(keys_a.ensure(m));
-    KMP_CUDA(vals_a.ensure(m));
+    if (h->adjwgt != nullptr) {
+      KMP_CUDA(vals_a.ensure(m));
+    }
     const uint32_t tiles = (m + kTileEdges - 1) / kTileEdges;
     KMP_CUDA(flags.ensure(static_cast<size_t>(tiles) + 1)); // the leader flags are dead: reuse as tile_lo
     k_tile_owners<<<grid_for(static_cast<uint64_t>(tiles) + 1, 256), 256, 0, st>>>(n, m, h->xadj, tiles, flags.p);
@@ -281,30 +321,44 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   }
   // ---- 3. sort + reduce by key -----------------------------------------------------------------
   uint32_t c_m = 0;
-  KMP_CUDA(cg->xadj.ensure(static_cast<size_t>(c_n) + 1));
+  KMP_CUDA(cg->xadj.alloc(static_cast<size_t>(c_n) + 1, st));
   if (cut > 0) {
     const int items = static_cast<int>(cut);
     KMP_CUDA(keys_b.ensure(cut));
     KMP_CUDA(vals_b.ensure(cut));
     cub::DoubleBuffer<unsigned long long> dk(keys_a.p, keys_b.p);
-    cub::DoubleBuffer<int32_t> dv(vals_a.p, vals_b.p);
-    KMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, items, 0, static_cast<int>(bits), st));
-    KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
-    KMP_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, dk, dv, items, 0, static_cast<int>(bits), st));
-    // unique keys and summed weights go to the idle halves of the double buffers
-    unsigned long long *uk = dk.Alternate();
-    int32_t *uw = dv.Alternate();
     uint32_t *num_runs = reinterpret_cast<uint32_t *>(counter.p + 1);
-    KMP_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, dk.Current(), uk, dv.Current(), uw, num_runs,
-                                            cub::Sum(), items, st));
-    KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
-    KMP_CUDA(cub::DeviceReduce::ReduceByKey(h->cub_tmp.p, tmp_bytes, dk.Current(), uk, dv.Current(), uw, num_runs,
-                                            cub::Sum(), items, st));
+    unsigned long long *uk = nullptr; // unique keys: the idle half of the key double buffer
+    int32_t *uw = nullptr;            // their weights
+    if (h->adjwgt != nullptr) {
+      cub::DoubleBuffer<int32_t> dv(vals_a.p, vals_b.p);
+      KMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, items, 0, static_cast<int>(bits), st));
+      KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
+      KMP_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp.p, tmp_bytes, dk, dv, items, 0, static_cast<int>(bits), st));
+      uk = dk.Alternate();
+      uw = dv.Alternate();
+      KMP_CUDA(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, dk.Current(), uk, dv.Current(), uw, num_runs,
+                                              cub::Sum(), items, st));
+      KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
+      KMP_CUDA(cub::DeviceReduce::ReduceByKey(h->cub_tmp.p, tmp_bytes, dk.Current(), uk, dv.Current(), uw, num_runs,
+                                              cub::Sum(), items, st));
+    } else {
+      // unit edge weights (the finest, i.e. largest, level): sort the keys alone (8 instead of 12 bytes per
+      // item and pass); the weight of a coarse edge is the length of its run
+      KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, dk, items, 0, static_cast<int>(bits), st));
+      KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
+      KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp_bytes, dk, items, 0, static_cast<int>(bits), st));
+      uk = dk.Alternate();
+      uw = vals_b.p;
+      KMP_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, dk.Current(), uk, uw, num_runs, items, st));
+      KMP_CUDA(h->cub_tmp.ensure(std::max<size_t>(tmp_bytes, 1)));
+      KMP_CUDA(cub::DeviceRunLengthEncode::Encode(h->cub_tmp.p, tmp_bytes, dk.Current(), uk, uw, num_runs, items, st));
+    }
     KMP_CUDA(cudaMemcpyAsync(&c_m, num_runs, 4, cudaMemcpyDeviceToHost, st));
     KMP_CUDA(cudaStreamSynchronize(st));
     // ---- 4. CSR assembly -------------------------------------------------------------------------
-    KMP_CUDA(cg->adjncy.ensure(c_m));
-    KMP_CUDA(cg->adjwgt.ensure(c_m));
+    KMP_CUDA(cg->adjncy.alloc(c_m, st));
+    KMP_CUDA(cg->adjwgt.alloc(c_m, st));
     KMP_CUDA(cudaMemcpyAsync(cg->adjwgt.p, uw, static_cast<size_t>(c_m) * 4, cudaMemcpyDeviceToDevice, st));
     k_coarse_offsets<<<grid_for(static_cast<uint64_t>(c_n) + 1, 256), 256, 0, st>>>(c_n, c_m, uk, shift, cg->xadj.p);
     k_coarse_targets<<<grid_for(c_m, 256), 256, 0, st>>>(c_m, uk, shift, cg->adjncy.p);
@@ -312,8 +366,8 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
     KMP_CUDA(cudaGetLastError());
   } else {
     KMP_CUDA(cudaMemsetAsync(cg->xadj.p, 0, (static_cast<size_t>(c_n) + 1) * 4, st));
-    KMP_CUDA(cg->adjncy.ensure(1));
-    KMP_CUDA(cg->adjwgt.ensure(1));
+    KMP_CUDA(cg->adjncy.alloc(1, st));
+    KMP_CUDA(cg->adjwgt.alloc(1, st));
   }
   cg->c_m = c_m;
   KMP_CUDA(cudaEventRecord(ev1, st));

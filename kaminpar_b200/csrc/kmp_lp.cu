@@ -1517,6 +1517,12 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ct_rank.release();
   h->ct_cl.release();
   h->ct_counter.release();
+  {
+    cudaMemPool_t pool = nullptr; // blocks cached for coarse graphs (kmp_contract.cuh)
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+      cudaMemPoolTrimTo(pool, 0);
+    }
+  }
   h->slot_state_clean = false;
   return KMP_OK;
 }
