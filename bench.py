@@ -340,13 +340,17 @@ def main():
         part0 = rng.integers(0, k, n).astype(np.uint32)
         mbw = ctx.partition.max_block_weights()
 
+    sharded_moved = []  # per-round move counts of the last sharded step (identical on every rank)
+
     def run_resident():
         if refine_handle is not None:
             refine_handle.upload_partition(part0)
             return refine_handle.refine(k, mbw, None)[2]
         if sharded is None:
             return handle.cluster(mcw, fetch=False)[1]
-        return sharded.compute_clustering(mcw, fetch=False)[2]
+        _, moved, st_sh = sharded.compute_clustering(mcw, fetch=False)
+        sharded_moved[:] = moved
+        return st_sh
 
     def barrier():
         if world > 1:
@@ -494,7 +498,9 @@ def main():
         "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": wl, "n": n, "m_directed": m, "k": k, "mode": args.mode,
-                   "max_cluster_weight": mcw, "iterations": last.iterations, "moved": last.moved_list(),
+                   "max_cluster_weight": mcw,
+                   "iterations": len(sharded_moved) if world > 1 else last.iterations,
+                   "moved": list(sharded_moved) if world > 1 else last.moved_list(),
                    "num_clusters": last.num_clusters, "l2": "inputs_larger_than_l2" if m * 4 > 126e6 else "small_input",
                    "parallelism": "single" if world == 1 else f"frontier-sharded x{world} (replicated labels, NCCL all-gather of proposals)",
                    "subrounds": ctx.engine.sync_subrounds},
