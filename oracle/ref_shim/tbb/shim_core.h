@@ -34,7 +34,6 @@
 #include <type_traits>
 #include <utility>
 #include <array>
-#include <cstdlib>
 #include <vector>
 
 namespace tbb {
