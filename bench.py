@@ -488,7 +488,7 @@ def main():
     }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         eps, dt, kind, cores, desc = cpu_reference_run(wl, args.cpu_steps, 1)
         cpu = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
 
