@@ -41,9 +41,15 @@ WORKLOADS = {
     "grid256": ("grid", dict(nx=256), 64),
     "rgg24": ("rgg", dict(n=1 << 24, seed=1), 64),
     "rgg20": ("rgg", dict(n=1 << 20, seed=1), 64),
+    # configs[4]: road-like planar graph, ~23 M vertices / ~56 M directed edges (SURVEY.md §8d input 5)
+    "road": ("road", dict(side=3500, seed=1, delete_frac=0.3, subdivide_frac=0.65), 256),
+    "road_small": ("road", dict(side=1000, seed=1, delete_frac=0.3, subdivide_frac=0.65), 256),
 }
-CPU_SAMPLE = {"rmat22": "rmat20", "rmat24": "rmat20", "rmat20": "rmat18", "rmat18": "rmat18",
-              "grid512": "grid256", "grid256": "grid256", "rgg24": "rgg20", "rgg20": "rgg20"}
+# Workload the CPU reference runs for a given GPU workload. Like for like wherever the reference finishes a
+# step in about a second (R-MAT 22: ~1.3 s/step on the box's host cores); only the three largest inputs
+# use a smaller graph of the same family so that `--impl reference --steps K --warmup W` (plus the thread
+# sweep) still ends within a few minutes -- the line's config says so ("cpu_sample").
+CPU_SAMPLE = {"rmat24": "rmat22", "grid512": "grid256", "rgg24": "rgg20", "road": "road_small"}
 
 
 def peaks():
@@ -72,6 +78,10 @@ def generate(name, device):
         adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
     elif kind == "rgg":
         g = G.rgg2d(args["n"], args["seed"], device=device)
+        xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)
+        adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
+    elif kind == "road":
+        g = G.road_like(args["side"], args["seed"], args["delete_frac"], args["subdivide_frac"], device=device)
         xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)
         adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
     else:
@@ -130,41 +140,55 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _cpu_worker(name, mode, steps, warmup):
-    """Run oracle/cpu_baseline_worker.py on a bounded sample of workload `name` in a child process that
-    never loads torch (isolation: see the worker's header). Returns
-    (units_per_s, s_per_step, kind, cores, description)."""
+def _cpu_worker(name, mode, steps, warmup, host_graph=None):
+    """Run oracle/cpu_baseline_worker.py on workload `name` (or its CPU_SAMPLE stand-in) in a child process
+    that never loads torch (isolation: see the worker's header). `host_graph` = (xadj, adjncy, k) numpy
+    arrays of `name` itself if the caller already has them. Returns
+    (units_per_s, s_per_step, kind, cores, description, extra) with extra = host cores + thread sweep."""
     import subprocess
     import tempfile
 
     sample = CPU_SAMPLE.get(name, name)
-    xadj, adj, k = generate(sample, "cpu")
+    if sample == name and host_graph is not None:
+        xadj_np, adj_np, k = host_graph
+    else:
+        import torch
+
+        # generation is not timed: use the GPU for it when there is one (same generator, same seed)
+        gen_dev = "cuda" if torch.cuda.is_available() else "cpu"
+        xadj, adj, k = generate(sample, gen_dev)
+        xadj_np, adj_np = xadj.cpu().numpy(), adj.cpu().numpy()
+        del xadj, adj
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "sample.npz")
-        np.savez(path, xadj=xadj.numpy().astype(np.uint32), adjncy=adj.numpy().astype(np.uint32), k=np.array([k]))
-        del xadj, adj
+        np.savez(path, xadj=np.asarray(xadj_np).astype(np.uint32), adjncy=np.asarray(adj_np).astype(np.uint32),
+                 k=np.array([k]))
+        del xadj_np, adj_np
         last_err = ""
+        env = dict(os.environ, OMP_STACKSIZE=os.environ.get("OMP_STACKSIZE", "64M"))
+        env.pop("OMP_NUM_THREADS", None)  # torchrun exports 1; the worker sizes its team from the affinity mask
         for extra in ([], ["serial"]):  # second try: the serial stand-in (1 core), should the OpenMP one fail
             r = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline_worker", path, mode, str(steps), str(warmup)]
-                               + extra, cwd=ROOT, capture_output=True, text=True,
-                               env=dict(os.environ, OMP_STACKSIZE=os.environ.get("OMP_STACKSIZE", "64M")))
+                               + extra, cwd=ROOT, capture_output=True, text=True, env=env)
             lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and lines:
                 d = json.loads(lines[-1])
-                return d["value"], d["seconds_per_step"], d["kind"], d["cores"], f"{sample}: {d['desc']}"
+                more = {"host_cores": d.get("host_cores"), "thread_sweep": d.get("thread_sweep"),
+                        "workload": sample, "same_workload": sample == name}
+                return d["value"], d["seconds_per_step"], d["kind"], d["cores"], f"{sample}: {d['desc']}", more
             last_err = f"rc={r.returncode} {r.stderr[-300:]}"
     raise RuntimeError("CPU baseline worker failed: " + last_err)
 
 
-def cpu_reference_run(name, steps, warmup):
+def cpu_reference_run(name, steps, warmup, host_graph=None):
     """The reference's own CPU path (oracle/_ref: unmodified sources on the host cores through the OpenMP
-    stand-in for oneTBB; serial stand-in or the oracle port if that did not travel), bounded sample."""
-    return _cpu_worker(name, "lp", steps, warmup)
+    stand-in for oneTBB; serial stand-in or the oracle port if that did not travel)."""
+    return _cpu_worker(name, "lp", steps, warmup, host_graph)
 
 
-def cpu_contraction_run(name, steps, warmup):
-    """contract_clustering of the unmodified reference (oracle/_ref) or the numpy port, bounded sample."""
-    return _cpu_worker(name, "contraction", steps, warmup)
+def cpu_contraction_run(name, steps, warmup, host_graph=None):
+    """contract_clustering of the unmodified reference (oracle/_ref) or the numpy port."""
+    return _cpu_worker(name, "contraction", steps, warmup, host_graph)
 
 
 def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
@@ -235,8 +259,9 @@ def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
                              "the radix passes over the inter-cluster edges are not algorithmic bytes"},
     }
     if not args.no_cpu_baseline:
-        eps, dt, kind, cores, desc = cpu_contraction_run(args.workload, args.cpu_steps, 1)
-        line["cpu_baseline"] = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
+        eps, dt, kind, cores, desc, more = cpu_contraction_run(args.workload, args.cpu_steps, 1,
+                                                               (g_host.xadj, g_host.adjncy, k))
+        line["cpu_baseline"] = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc, **more}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -266,13 +291,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        eps, dt, kind, cores, desc = cpu_reference_run(args.workload, args.steps, max(args.warmup, 1))
+        eps, dt, kind, cores, desc, more = cpu_reference_run(args.workload, args.steps, max(args.warmup, 1))
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": eps, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "k": k, "mode": "clustering", "sample": CPU_SAMPLE.get(args.workload)},
-            "cpu_baseline": {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
+            "config": {"workload": args.workload, "k": k, "mode": "clustering",
+                       "cpu_sample": more["workload"], "same_workload": more["same_workload"]},
+            "cpu_baseline": {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc, **more},
             "e2e": {"value": eps, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }), flush=True)
         # two OpenMP runtimes live in this process (torch's and the stand-in's): skip interpreter teardown
@@ -489,8 +515,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
-        eps, dt, kind, cores, desc = cpu_reference_run(wl, args.cpu_steps, 1)
-        cpu = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc}
+        eps, dt, kind, cores, desc, more = cpu_reference_run(wl, args.cpu_steps, 1, (g_host.xadj, g_host.adjncy, k))
+        cpu = {"value": eps, "unit": unit, "cores": cores, "kind": kind, "sample": desc, **more}
 
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

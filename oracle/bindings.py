@@ -353,3 +353,26 @@ def oracle_sync_select_all(mode, g, labels, weights, max_weights=None, max_clust
         C.c_int32(max_cluster_weight), _opt(min_weights, np.int32), C.c_int(seed), C.c_uint32(call),
         C.c_uint32(iteration), tgt.ctypes.data_as(C.c_void_p), fav.ctypes.data_as(C.c_void_p))
     return tgt, fav
+
+
+def oracle_seq_select_all(mode, g, labels, weights, max_weights=None, max_cluster_weight=0, min_weights=None,
+                          check_target=None, check_favored=None):
+    """The reference-pinned `seq` selection code on frozen state (lpo_seq_select_all). Returns a dict with
+    target, favored, num_ties, num_fav_ties, check_in_ties, check_fav_in_ties."""
+    labels = np.ascontiguousarray(labels, np.uint32)
+    weights = np.ascontiguousarray(weights, np.int32)
+    tgt = np.zeros(g.n, np.uint32)
+    fav = np.zeros(g.n, np.uint32)
+    nt = np.zeros(g.n, np.uint32)
+    nft = np.zeros(g.n, np.uint32)
+    cin = np.ones(g.n, np.uint8)
+    cfin = np.ones(g.n, np.uint8)
+    oracle().lpo_seq_select_all(
+        C.c_int(mode), C.c_uint32(g.n), g.xadj.ctypes.data_as(C.c_void_p), g.adjncy.ctypes.data_as(C.c_void_p),
+        _opt(g.vwgt, np.int32), _opt(g.adjwgt, np.int32), labels.ctypes.data_as(C.c_void_p),
+        weights.ctypes.data_as(C.c_void_p), C.c_uint32(len(weights)), _opt(max_weights, np.int32),
+        C.c_int32(max_cluster_weight), _opt(min_weights, np.int32), _opt(check_target, np.uint32),
+        _opt(check_favored, np.uint32), tgt.ctypes.data_as(C.c_void_p), fav.ctypes.data_as(C.c_void_p),
+        nt.ctypes.data_as(C.c_void_p), nft.ctypes.data_as(C.c_void_p), cin.ctypes.data_as(C.c_void_p),
+        cfin.ctypes.data_as(C.c_void_p))
+    return dict(target=tgt, favored=fav, num_ties=nt, num_fav_ties=nft, check_in_ties=cin, check_fav_in_ties=cfin)

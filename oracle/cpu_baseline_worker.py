@@ -20,6 +20,7 @@ import sys
 import time
 
 os.environ.setdefault("OMP_STACKSIZE", "64M")  # before anything loads libgomp
+os.environ.pop("OMP_NUM_THREADS", None)  # torchrun sets it to 1; the thread count is chosen below
 
 import numpy as np  # noqa: E402
 
@@ -28,6 +29,16 @@ sys.path.insert(0, ROOT)
 
 from kaminpar_b200.graph import CSRGraph  # noqa: E402  (numpy only)
 from oracle import bindings as B  # noqa: E402
+
+
+SWEEP = []  # thread counts tried for the reference and their time per step
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_lp(g, k, steps, warmup, serial):
@@ -39,14 +50,18 @@ def run_lp(g, k, steps, warmup, serial):
         kind, fn = "reference", (lambda: B.ref_lp_cluster(g, 0, mcw, parallel=True))
         # the thread count that is fastest for the reference on this box (all cores is not always best:
         # the graph is first-touched by one thread), so that the baseline is not handicapped
-        avail = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+        # cores this process may run on -- NOT OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to
+        # its children, which made the round-1 reference arm single-threaded at N > 1
+        avail = host_cores()
         best = None
-        for t in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 16)}, reverse=True):
+        for t in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 32), min(avail, 16), min(avail, 8)},
+                        reverse=True):
             B.ref_omp().kmpref_set_num_threads(t)
             fn()
             t0 = time.perf_counter()
             fn()
             dt = time.perf_counter() - t0
+            SWEEP.append({"threads": t, "seconds_per_step": dt})
             if best is None or dt < best[0]:
                 best = (dt, t)
         cores = best[1]
@@ -94,7 +109,7 @@ def main():
     else:
         units, dt, kind, cores, desc = run_contraction(g, k, steps, warmup)
     print(json.dumps({"value": units / dt, "seconds_per_step": dt, "kind": kind, "cores": cores, "units": units,
-                      "desc": desc}), flush=True)
+                      "desc": desc, "host_cores": host_cores(), "thread_sweep": SWEEP}), flush=True)
     os._exit(0)
 
 

@@ -106,6 +106,18 @@ int lpo_sync_select_all(int mode, uint32_t n, const uint32_t *xadj, const uint32
                         uint32_t call_index, uint32_t iteration, uint32_t *out_target,
                         uint32_t *out_favored);
 
+/* ---- bridge: the reference-pinned `seq` selection code (ClusterPolicy / RefinePolicy::select_best_cluster,
+ * the code checked bit-for-bit against the unmodified reference) on the same frozen state. Outputs the
+ * reference's choice, the size of the tie set it draws from (UNIFORM) and whether check_target[u] /
+ * check_favored[u] lie in that set; see tests/test_bridge_sync_to_reference.py. */
+int lpo_seq_select_all(int mode, uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *vwgt,
+                       const int32_t *adjwgt, const uint32_t *labels, const int32_t *weights, uint32_t num_labels,
+                       const int32_t *max_weights, int32_t max_cluster_weight, const int32_t *min_weights,
+                       const uint32_t *check_target /*nullable*/, const uint32_t *check_favored /*nullable*/,
+                       uint32_t *out_target, uint32_t *out_favored /*nullable*/, uint32_t *out_num_ties,
+                       uint32_t *out_num_fav_ties /*nullable*/, uint8_t *out_check_in_ties /*nullable*/,
+                       uint8_t *out_check_fav_in_ties /*nullable*/);
+
 #ifdef __cplusplus
 }
 #endif
