@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define KMP_LP_ABI_VERSION 1
+#define KMP_LP_ABI_VERSION 2
 
 typedef enum {
   KMP_OK = 0,
@@ -59,19 +59,34 @@ typedef struct {
   uint32_t max_num_neighbors;      /* UINT32_MAX: scan at most this many neighbours per vertex */
   int32_t impl;                    /* accepted for API compatibility; every implementation choice of
                                       the reference has the same observable selection rule */
-  int32_t tie_breaking_strategy;   /* KMP_TIE_UNIFORM (GEOMETRIC is mapped to UNIFORM: both pick
-                                      uniformly among maximal candidates) */
-  int32_t two_hop_strategy;        /* clusterer only */
+  int32_t tie_breaking_strategy;   /* KMP_TIE_UNIFORM. KMP_TIE_GEOMETRIC (sequential coin flips in rating-map
+                                      insertion order, lp_clusterer.cc:252-278) has no order-free restatement:
+                                      KMP_ERR_UNSUPPORTED under schedule KMP_SCHEDULE_SYNC, implemented by
+                                      KMP_SCHEDULE_SEQ_STRICT */
+  int32_t two_hop_strategy;        /* clusterer only. SYNC: DISABLE, MATCH_THREADWISE (default) and
+                                      CLUSTER_THREADWISE; the global MATCH / CLUSTER variants
+                                      (label_propagation.h:1030-1191, an id-ordered chain of CAS hand-offs) are
+                                      KMP_ERR_UNSUPPORTED under SYNC and implemented by SEQ_STRICT */
   double two_hop_threshold;        /* 0.5 */
-  int32_t isolated_nodes_strategy; /* clusterer only */
-  int32_t relabel_before_second_phase; /* accepted, no effect (no second phase on the GPU) */
+  int32_t isolated_nodes_strategy; /* clusterer only; all five values */
+  int32_t relabel_before_second_phase; /* must be 0 (the default, presets.cc:147) under SYNC: there is no second
+                                      phase to relabel for; non-zero = KMP_ERR_UNSUPPORTED */
   /* engine */
   int32_t seed;                /* Random::reseed() analogue; enters every hash key */
   uint32_t sync_subrounds;     /* S: hashed sub-rounds per degree group and iteration (8) */
   uint32_t sync_granule_log2;  /* vertices u >> g share a sub-round (4) */
   uint32_t sync_commit_passes; /* commit passes crediting departures: 1 clusterer, 4 refiner */
   int32_t device;              /* CUDA device ordinal, -1 = current */
+  int32_t schedule;            /* KMP_SCHEDULE_SYNC (default) or KMP_SCHEDULE_SEQ_STRICT */
 } kmp_lp_config;
+
+/* Visit schedules. SYNC: deterministic synchronous sub-rounds, any size, any number of GPUs
+ * (DESIGN.md §3). SEQ_STRICT: the reference's own one-thread visit order, rating-map insertion order and
+ * libstdc++ mt19937 draws, executed by ONE thread block -- bit-identical to the unmodified reference at one
+ * thread (label_propagation.h:1863-1937, kaminpar-common/random.h:64-147); meant for small inputs
+ * (n <= KMP_SEQ_STRICT_MAX_N), e.g. BASELINE config 1. */
+enum { KMP_SCHEDULE_SYNC = 0, KMP_SCHEDULE_SEQ_STRICT = 1 };
+#define KMP_SEQ_STRICT_MAX_N (1u << 20)
 
 typedef struct {
   uint32_t iterations;       /* LP rounds executed */
@@ -85,13 +100,16 @@ typedef struct {
   float sweep_ms;            /* CUDA-event time spent in the sweep kernels only (if timing enabled) */
   uint64_t sweep_launches;   /* number of sweep-kernel launches */
   uint64_t kernel_launches;  /* all kernel launches of the call */
-  /* per kernel tier (0: deg<8 sweep_thread, 1: deg<32 sweep_warp, 2: deg<256 sweep_warp_hash,
-   * 3: deg<2048 sweep_group, 4: deg>=2048 sweep_hub_aggregate+sweep_hub_select; 5..7 unused) */
+  /* per kernel tier (0: deg<8 sweep_thread, 1: deg<32 sweep_warp, 2: deg<256 sweep_team<32>,
+   * 3: deg<1024 sweep_team<128>, 4: deg<4096 sweep_team<512>, 5: deg<8192 sweep_team<1024>,
+   * 6: deg>=8192 sweep_hub_aggregate+partial+final; 7 unused) */
   uint64_t group_edges[8];
   uint64_t group_nodes[8];
   uint64_t group_launches[8];
-  float group_sweep_ms[8];   /* only when timing is enabled: [0..4] sweep tiers, [5] commit-rule kernels,
-                              * [6] apply + activate */
+  float group_sweep_ms[12];  /* only when timing is enabled: [0..6] sweep tiers, [8] commit-rule kernels,
+                              * [9] apply, [10] push activation, [11] stamp ageing */
+  uint32_t pull_rounds;      /* LP rounds whose sweeps derived the active flags from the move stamps */
+  uint32_t push_rounds;      /* LP rounds in which movers flagged their neighbours */
 } kmp_lp_stats;
 
 typedef struct kmp_lp_handle kmp_lp_handle;

@@ -48,13 +48,26 @@ int fail(int code, const std::string &msg) {
   } while (0)
 
 constexpr int kNumGroups = 4; // degree groups of the schedule
-constexpr int kNumTiers = 5;  // kernel tiers: group 3 is split at degree 2048
+constexpr int kNumTiers = 7;  // kernel tiers: group 3 (deg >= 256) is split into four tiers
+constexpr int kHubTier = 6;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
+constexpr uint32_t kHubMinDegree = 8192;
 constexpr int kSMs = 148;
 constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512)
+constexpr int kTagCommit = 8, kTagApply = 9, kTagPush = 10, kTagMisc = 11; // timing slots besides the tiers
+
+// kernel tier of a vertex of degree d >= 1 (tiers 3..6 are degree group 3 of the schedule)
+__host__ __device__ inline uint32_t tier_of(uint32_t d) {
+  return d < 8 ? 0u : d < 32 ? 1u : d < 256 ? 2u : d < 1024 ? 3u : d < 4096 ? 4u : d < kHubMinDegree ? 5u : 6u;
+}
+inline int group_of_tier(int tier) { return tier < 3 ? tier : 3; }
 
 template <typename T> struct DevBuf {
   T *p = nullptr;
   size_t cap = 0; // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
   cudaError_t ensure(size_t n) {
     if (n <= cap) {
       return cudaSuccess;
@@ -89,6 +102,16 @@ struct kmp_lp_handle {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
   std::vector<int> sweep_event_group;
   uint64_t group_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // packed (label, stamp) gather array of the sweeps (lp_device.cuh): 4 B per vertex while labels fit 24 bits
+  // (n <= 2^24 clusterer / k <= 2^24 refiner), else 8 B
+  DevBuf<unsigned char> labg;
+  bool p64 = false;
+  bool stamps_ok = false;        // 4 * S sub-rounds fit the stamp code (else push activation only)
+  bool pull_this = true, pull_next = true; // activation mode of the running / the next LP round
+  uint32_t moved_hist[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; // accepted moves of the two previous rounds
+  uint32_t visited_total = 0;    // vertices on the work lists
+  DevBuf<uint32_t> queue;        // work-queue cursors of the team kernels: [tier][sub-round], zeroed per round
+  DevBuf<uint32_t> t4_hit;       // hub tier: per list entry "a neighbour moved since the last visit"
   size_t sweep_events_used = 0;
 
   // graph
@@ -139,7 +162,8 @@ struct kmp_lp_handle {
   uint32_t hub_cap_pct = 300; // tier-4 table slots per 100 labels (KMP_HUB_CAP_PCT overrides, for experiments)
   DevBuf<unsigned long long> hub_tab; // packed (key << 32 | rating) entries, kEmpty64 when unused
   uint32_t mover_cap = 0;
-  uint32_t cur_subround = 0;
+  uint32_t cur_subround = 0; // hashed class of the running sub-round
+  uint32_t cur_sg = 0;       // running sub-round index in [0, 4 * S): queue cursor and stamp code
   DevBuf<uint8_t> sort_keys_in, sort_keys_out;
   DevBuf<uint32_t> sort_vals_in;
   DevBuf<unsigned char> cub_tmp;
@@ -152,10 +176,12 @@ struct kmp_lp_handle {
 
   uint32_t call_counter = 0;
   uint64_t kernel_launches = 0, sweep_launches = 0;
+  uint32_t pull_rounds = 0, push_rounds = 0;
   // frontier sharding (one process per GPU): this rank sweeps slice `rank` of `world` of every list
   uint32_t rank = 0, world = 1;
   // stepping API state
   int step_mode = -1;
+  uint32_t step_iter = 0; // LP round of the stepping API
   uint32_t step_labels = 0;
   int32_t step_mcw = 0;
   bool step_has_min = false, step_has_comm = false;
@@ -201,8 +227,7 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, GroupS
     if (d == 0 || !(d < large_degree_threshold)) {
       key = kNumTiers * S; // never visited (label_propagation.h:1795, :1914-1915)
     } else {
-      const uint32_t tier = d < kTier4MinDegree ? degree_group(d) : 4u;
-      key = tier * S + subround_of(u, granule_log2, base_sr, gs.s[degree_group(d)]);
+      key = tier_of(d) * S + subround_of(u, granule_log2, base_sr, gs.s[degree_group(d)]);
     }
     keys[u] = static_cast<uint8_t>(key);
     vals[u] = u;
@@ -228,13 +253,32 @@ __global__ void k_gather_degrees(uint32_t cnt, const uint32_t *list, const uint3
   }
 }
 
-__global__ void k_init_cluster(uint32_t n, const int32_t *vwgt, uint32_t *label, int32_t *weight, uint32_t *favored,
-                               uint8_t *active) {
+template <bool P64>
+__global__ void k_init_cluster(uint32_t n, const int32_t *vwgt, uint32_t *label, void *labg, int32_t *weight,
+                               uint32_t *favored, uint8_t *active) {
   for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     label[u] = u; // reset_state, label_propagation.h:1194-1220 with initial_cluster(u) = u
+    static_cast<typename LabG<P64>::word *>(labg)[u] = LabG<P64>::pack(u, 0);
     favored[u] = u;
     weight[u] = vwgt != nullptr ? vwgt[u] : 1;
     active[u] = 1;
+  }
+}
+// packed gather words from plain labels, stamp 0 (refiner start, T0 hook)
+template <bool P64> __global__ void k_pack_labels(uint32_t n, const uint32_t *label, void *labg) {
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    static_cast<typename LabG<P64>::word *>(labg)[u] = LabG<P64>::pack(label[u], 0);
+  }
+}
+// start of round r >= 2: forget the moves of round r - 2 (their stamps carry the parity of round r)
+template <bool P64> __global__ void k_age_stamps(uint32_t n, void *labg, uint32_t parity) {
+  typename LabG<P64>::word *g = static_cast<typename LabG<P64>::word *>(labg);
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const typename LabG<P64>::word w = g[u];
+    const uint32_t st = LabG<P64>::stamp(w);
+    if (st != 0 && ((st - 1u) >> kStampBits) == parity) {
+      g[u] = LabG<P64>::pack(LabG<P64>::label(w), 0);
+    }
   }
 }
 __global__ void k_fill_u64(uint64_t n, unsigned long long *p, unsigned long long v) {
@@ -430,39 +474,57 @@ inline uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t max_b
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(b, max_blocks)));
 }
 
-template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int group, const SweepArgs &a) {
+template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS>
+void launch_team(kmp_lp_handle *h, const SweepArgs &a, int ctas_per_sm) {
+  const size_t smem = static_cast<size_t>(SLOTS) * TEAMS * 8;
+  const uint32_t want = (a.list_size + TEAMS - 1) / TEAMS;
+  const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(want, static_cast<uint32_t>(kSMs * ctas_per_sm)));
+  sweep_team<MODE, EW, P64, T, SLOTS, TEAMS><<<blocks, T * TEAMS, smem, h->stream>>>(a);
+}
+
+// dynamic shared memory opt-in of the team kernels (per device; called from kmp_lp_create)
+template <int MODE, bool EW, bool P64> void configure_team_kernels() {
+  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 8 * 8);
+  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 128, 2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 4 * 8);
+  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 512, 8192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 1024, 16384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+}
+
+template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle *h, int tier, const SweepArgs &a) {
   if (a.list_size == 0) {
     return cudaSuccess;
   }
-  switch (group) {
+  switch (tier) {
   case 0:
-    sweep_thread<MODE, EW><<<grid_for(a.list_size, 256), 256, 0, h->stream>>>(a);
+    sweep_thread<MODE, EW, P64><<<grid_for(a.list_size, 256), 256, 0, h->stream>>>(a);
     break;
   case 1:
-    sweep_warp<MODE, EW><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->stream>>>(a);
+    sweep_warp<MODE, EW, P64><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->stream>>>(a);
     break;
-  case 2:
-    sweep_warp_hash<MODE, EW>
-        <<<grid_for(static_cast<uint64_t>(a.list_size) * 32, kWarpsPerBlockG2 * 32), kWarpsPerBlockG2 * 32, 0,
-           h->stream>>>(a);
+  case 2: // deg < 256: one warp per vertex, 512 slots
+    launch_team<MODE, EW, P64, 32, 512, 8>(h, a, 7);
     break;
-  case 3: {
-    const size_t smem = static_cast<size_t>(kGroupTableSlots) * kGroupsPerBlock * 8;
-    const uint32_t blocks = grid_for(static_cast<uint64_t>((a.list_size + kGroupsPerBlock - 1) / kGroupsPerBlock) *
-                                         kGroupThreads * kGroupsPerBlock,
-                                     kGroupThreads * kGroupsPerBlock, kSMs * 6);
-    sweep_group<MODE, EW><<<blocks, kGroupThreads * kGroupsPerBlock, smem, h->stream>>>(a);
+  case 3: // deg < 1024: 128 threads per vertex, 2048 slots
+    launch_team<MODE, EW, P64, 128, 2048, 4>(h, a, 3);
     break;
-  }
+  case 4: // deg < 4096: 512 threads per vertex, 8192 slots
+    launch_team<MODE, EW, P64, 512, 8192, 1>(h, a, 3);
+    break;
+  case 5: // deg < 8192: 1024 threads per vertex, 16384 slots
+    launch_team<MODE, EW, P64, 1024, 16384, 1>(h, a, 1);
+    break;
   default: {
     HubArgs hb{};
     const uint32_t s_idx = h->cur_subround;
-    hb.table_off = h->t4_table_off.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
+    const uint32_t S = h->lists_S;
+    const uint32_t first = h->list_off[kHubTier * S + s_idx] - h->list_off[kHubTier * S];
+    hb.table_off = h->t4_table_off.p + first;
     hb.g_tab = h->hub_tab.p;
     hb.cap_pct = h->hub_cap_pct;
     hb.rank = h->rank;
     hb.world = h->world;
-    hb.sel_begin = h->t4_sel_begin.p + (h->list_off[4 * h->lists_S + s_idx] - h->list_off[4 * h->lists_S]);
+    hb.sel_begin = h->t4_sel_begin.p + first;
+    hb.hit = h->t4_hit.p + first;
     // one aggregate + partial-select pair per wave; all waves share the table memory (kept clean by the select)
     for (uint32_t w = h->t4_wave_off[s_idx]; w < h->t4_wave_off[s_idx + 1]; ++w) {
       const kmp_lp_handle::HubWave &wv = h->t4_waves[w];
@@ -473,7 +535,7 @@ template <int MODE, bool EW> cudaError_t launch_sweep_t(kmp_lp_handle *h, int gr
       hb.item_deg = h->t4_item_deg.p + wv.item_lo;
       hb.num_items = wv.item_hi - wv.item_lo;
       hb.queue = h->ctr32.p + 64 + w; // zeroed with the other per-round counters
-      sweep_hub_aggregate<MODE, EW><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
+      sweep_hub_aggregate<MODE, EW, P64><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
       hb.sel_entry = h->t4_sel_entry.p + wv.sel_lo;
       hb.sel_piece = h->t4_sel_piece.p + wv.sel_lo;
       hb.num_sel_items = wv.sel_hi - wv.sel_lo;
@@ -515,24 +577,32 @@ void timed_end(kmp_lp_handle *h, int idx) {
   }
 }
 
-cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int group, const SweepArgs &a_in) {
+// tier: kernel tier 0..6 of the list in `a_in`
+cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int tier, const SweepArgs &a_in) {
   if (a_in.list_size == 0) {
     return cudaSuccess;
   }
   SweepArgs a = a_in;
-  a.counters = h->ctr64.p + group;
-  const int ev = timed_begin(h, group);
+  a.counters = h->ctr64.p + tier;
+  a.queue = h->queue.p + static_cast<size_t>(tier) * kNumGroups * h->lists_S + h->cur_sg;
+  const int ev = timed_begin(h, tier);
   const bool ew = h->adjwgt != nullptr;
+  const int variant = (mode << 2) | (ew ? 2 : 0) | (h->p64 ? 1 : 0);
   cudaError_t e;
-  if (mode == 0) {
-    e = ew ? launch_sweep_t<0, true>(h, group, a) : launch_sweep_t<0, false>(h, group, a);
-  } else {
-    e = ew ? launch_sweep_t<1, true>(h, group, a) : launch_sweep_t<1, false>(h, group, a);
+  switch (variant) {
+  case 0: e = launch_sweep_t<0, false, false>(h, tier, a); break;
+  case 1: e = launch_sweep_t<0, false, true>(h, tier, a); break;
+  case 2: e = launch_sweep_t<0, true, false>(h, tier, a); break;
+  case 3: e = launch_sweep_t<0, true, true>(h, tier, a); break;
+  case 4: e = launch_sweep_t<1, false, false>(h, tier, a); break;
+  case 5: e = launch_sweep_t<1, false, true>(h, tier, a); break;
+  case 6: e = launch_sweep_t<1, true, false>(h, tier, a); break;
+  default: e = launch_sweep_t<1, true, true>(h, tier, a); break;
   }
   timed_end(h, ev);
   ++h->kernel_launches;
   ++h->sweep_launches;
-  ++h->group_launches[group];
+  ++h->group_launches[tier];
   return e;
 }
 
@@ -543,8 +613,9 @@ int ensure_lists(kmp_lp_handle *h) {
     return KMP_OK;
   }
   if (kNumTiers * S + 1 > 255) {
-    return fail(KMP_ERR_INVALID, "sync_subrounds too large (max 50)");
+    return fail(KMP_ERR_INVALID, "sync_subrounds too large (max 36)");
   }
+  h->stamps_ok = kNumGroups * S <= kMaxStampSubrounds; // else: push activation only
   const uint32_t n = h->n;
   const uint32_t nkeys = kNumTiers * S + 1;
   KMP_CUDA(h->sort_keys_in.ensure(n));
@@ -563,6 +634,7 @@ int ensure_lists(kmp_lp_handle *h) {
     KMP_CUDA(cudaMemcpyAsync(cnt, h->ctr32.p, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
     KMP_CUDA(cudaStreamSynchronize(h->stream));
     const uint64_t visited = static_cast<uint64_t>(cnt[0]) + cnt[1] + cnt[2] + cnt[3];
+    h->visited_total = static_cast<uint32_t>(visited);
     for (int q = 0; q < 4; ++q) {
       gs.s[q] = (16ull * cnt[q] >= visited) ? S : std::max<uint32_t>(1, S / 4);
     }
@@ -594,13 +666,18 @@ int ensure_lists(kmp_lp_handle *h) {
     for (uint32_t t = 0; t < 3; ++t) {
       h->mover_cap = std::max(h->mover_cap, lsize(t, sr));
     }
-    h->mover_cap = std::max(h->mover_cap, lsize(3, sr) + lsize(4, sr));
+    uint32_t g3 = 0; // the tiers of degree group 3 share a sub-round
+    for (uint32_t t = 3; t < kNumTiers; ++t) {
+      g3 += lsize(t, sr);
+    }
+    h->mover_cap = std::max(h->mover_cap, g3);
   }
+  KMP_CUDA(h->queue.ensure(static_cast<size_t>(kNumTiers) * kNumGroups * S));
   h->max_list = h->mover_cap;
   h->max_degree = hist[300];
   // ---- tier 4 metadata: table regions and chunk work items per sub-round ------------------------
   {
-    const uint32_t t4_begin = h->list_off[4 * S], t4_end = h->list_off[5 * S];
+    const uint32_t t4_begin = h->list_off[kHubTier * S], t4_end = h->list_off[(kHubTier + 1) * S];
     const uint32_t t4_cnt = t4_end - t4_begin;
     h->t4_item_off.assign(S + 1, 0);
     h->t4_wave_off.assign(S + 1, 0);
@@ -619,7 +696,13 @@ int ensure_lists(kmp_lp_handle *h) {
       std::vector<uint32_t> deg(t4_cnt), toff(t4_cnt), sbeg(t4_cnt), ient, ichk, sent, spiece;
       h->t4_sel_off.assign(S + 1, 0);
       size_t max_sel = 0;
+      KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      KMP_CUDA(cudaStreamSynchronize(h->stream));
+      d_deg.release();
+      d_beg.release();
+      d_ids.release();
       // at most kMaxHubWaves work-queue cursors exist per LP round: coarsen the waves if necessary
+      // (the degrees must be on the host before this sum -- ADVICE r1)
       uint64_t wave_slots = h->hub_wave_slots;
       {
         uint64_t total = 0;
@@ -628,13 +711,8 @@ int ensure_lists(kmp_lp_handle *h) {
         }
         wave_slots = std::max<uint64_t>(wave_slots, total / (kMaxHubWaves / 2 - S) + 1);
       }
-      KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-      KMP_CUDA(cudaStreamSynchronize(h->stream));
-      d_deg.release();
-      d_beg.release();
-      d_ids.release();
       for (uint32_t sr = 0; sr < S; ++sr) {
-        const uint32_t lo = h->list_off[4 * S + sr] - t4_begin, hi = h->list_off[4 * S + sr + 1] - t4_begin;
+        const uint32_t lo = h->list_off[kHubTier * S + sr] - t4_begin, hi = h->list_off[kHubTier * S + sr + 1] - t4_begin;
         uint64_t slots = 0;
         kmp_lp_handle::HubWave wave{static_cast<uint32_t>(ient.size()), 0, static_cast<uint32_t>(sent.size()), 0};
         auto close_wave = [&]() {
@@ -679,7 +757,12 @@ int ensure_lists(kmp_lp_handle *h) {
         max_sel = std::max<size_t>(max_sel, sent.size() - h->t4_sel_off[sr]);
         h->t4_item_off[sr + 1] = static_cast<uint32_t>(ient.size());
       }
+      if (h->t4_waves.size() > kMaxHubWaves) {
+        return fail(KMP_ERR_UNSUPPORTED, "too many high-degree table waves (raise KMP_HUB_WAVE_SLOTS)");
+      }
       KMP_CUDA(h->t4_table_off.ensure(t4_cnt));
+      KMP_CUDA(h->t4_hit.ensure(t4_cnt));
+      KMP_CUDA(cudaMemsetAsync(h->t4_hit.p, 0, static_cast<size_t>(t4_cnt) * 4, h->stream));
       KMP_CUDA(h->t4_item_entry.ensure(ient.size()));
       KMP_CUDA(h->t4_item_chunk.ensure(ichk.size()));
       KMP_CUDA(cudaMemcpyAsync(h->t4_table_off.p, toff.data(), t4_cnt * 4, cudaMemcpyHostToDevice, h->stream));
@@ -771,6 +854,10 @@ SweepArgs make_sweep_args(kmp_lp_handle *h, const RunCtx &rc) {
   a.vwgt = h->vwgt;
   a.adjwgt = h->adjwgt;
   a.label = h->label.p;
+  a.labg = h->labg.p;
+  a.pull = false;
+  a.window = make_window(0, 0);
+  a.queue = h->queue.p;
   a.weight = h->weight.p;
   a.max_w = rc.mode == 1 ? h->maxw.p : nullptr;
   a.min_w = rc.has_min ? h->minw.p : nullptr;
@@ -797,6 +884,8 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
   c.adjncy = h->adjncy;
   c.vwgt = h->vwgt;
   c.label = h->label.p;
+  c.labg = h->labg.p;
+  c.stamp = 0;
   c.weight = h->weight.p;
   c.max_w = rc.mode == 1 ? h->maxw.p : nullptr;
   c.min_w = rc.has_min ? h->minw.p : nullptr;
@@ -822,11 +911,15 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
   return c;
 }
 
-// One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
+// A sub-round sg in [0, 4 * S) = (degree group, hashed class). Groups 0..2 have one work list (tier =
+// group); group 3 has the lists of tiers 3..6 (tier 6 = hubs, sharded round-robin instead of by range).
 struct SubRound {
   int group;
-  uint32_t sr, size_a, size_b; // full list sizes (tiers <= 3; tier 4)
-  uint32_t lo_a, hi_a;         // this rank's slice of list a
+  uint32_t sr;
+  int first_tier, last_tier;  // inclusive
+  uint32_t size[kNumTiers];   // full list sizes of the tiers of this sub-round (0 elsewhere)
+  uint32_t lo[kNumTiers], hi[kNumTiers]; // this rank's slice (range-sharded tiers)
+  uint32_t total;
 };
 
 SubRound subround_of_sg(const kmp_lp_handle *h, uint32_t sg) {
@@ -834,16 +927,30 @@ SubRound subround_of_sg(const kmp_lp_handle *h, uint32_t sg) {
   SubRound q{};
   q.group = static_cast<int>(sg / S);
   q.sr = sg % S;
-  q.size_a = h->list_off[sg + 1] - h->list_off[sg];
-  q.size_b = q.group == 3 ? h->list_off[4 * S + q.sr + 1] - h->list_off[4 * S + q.sr] : 0;
-  q.lo_a = static_cast<uint32_t>(static_cast<uint64_t>(q.size_a) * h->rank / h->world);
-  q.hi_a = static_cast<uint32_t>(static_cast<uint64_t>(q.size_a) * (h->rank + 1) / h->world);
+  q.first_tier = q.group < 3 ? q.group : 3;
+  q.last_tier = q.group < 3 ? q.group : kNumTiers - 1;
+  for (int t = q.first_tier; t <= q.last_tier; ++t) {
+    const uint32_t sz = h->list_off[t * S + q.sr + 1] - h->list_off[t * S + q.sr];
+    q.size[t] = sz;
+    q.total += sz;
+    if (t == kHubTier) { // every rank sees the whole hub list and takes entries i % world == rank
+      q.lo[t] = 0;
+      q.hi[t] = sz;
+    } else {
+      q.lo[t] = static_cast<uint32_t>(static_cast<uint64_t>(sz) * h->rank / h->world);
+      q.hi[t] = static_cast<uint32_t>(static_cast<uint64_t>(sz) * (h->rank + 1) / h->world);
+    }
+  }
   return q;
 }
 
 // capacity of one rank's proposal buffer for sub-round sg (identical on every rank)
 uint32_t subround_cap(const kmp_lp_handle *h, const SubRound &q) {
-  return (q.size_a + h->world - 1) / h->world + (q.size_b + h->world - 1) / h->world + 1;
+  uint32_t cap = 1;
+  for (int t = q.first_tier; t <= q.last_tier; ++t) {
+    cap += (q.size[t] + h->world - 1) / h->world;
+  }
+  return cap;
 }
 
 // sweep kernels of one sub-round over this rank's share of the lists
@@ -854,14 +961,17 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   sa.base_fav = sync_base(h->cfg.seed, h->call_counter, iter, SALT_FAV);
   sa.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   sa.accumulate = !h->stepping && rc.mode == 0; // refiner: accumulated by k_accumulate_movers (privatised)
+  sa.pull = h->pull_this;
+  sa.window = make_window(iter, sg);
   h->cur_subround = q.sr;
-  sa.list = h->order.p + h->list_off[sg] + q.lo_a;
-  sa.list_size = q.hi_a - q.lo_a;
-  KMP_CUDA(launch_sweep(h, rc.mode, q.group, sa));
-  if (q.size_b > 0) {
-    sa.list = h->order.p + h->list_off[4 * S + q.sr];
-    sa.list_size = q.size_b;
-    KMP_CUDA(launch_sweep(h, rc.mode, 4, sa));
+  h->cur_sg = sg;
+  for (int t = q.first_tier; t <= q.last_tier; ++t) {
+    if (q.size[t] == 0) {
+      continue;
+    }
+    sa.list = h->order.p + h->list_off[t * S + q.sr] + q.lo[t];
+    sa.list_size = q.hi[t] - q.lo[t];
+    KMP_CUDA(launch_sweep(h, rc.mode, t, sa));
   }
   return KMP_OK;
 }
@@ -870,14 +980,15 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
 int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
   CommitArgs ca = make_commit_args(h, rc);
   ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-  const uint32_t size = q.size_a + q.size_b;
+  ca.stamp = h->stamps_ok ? make_stamp(iter, sg) : 0;
+  const uint32_t size = q.total;
   const uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
   const uint32_t cgrid = grid_for(size, 256, kSMs * 8);
-  int ev = timed_begin(h, 5);
+  int ev = timed_begin(h, kTagCommit);
   if (rc.mode == 0) {
     commit_cluster_classify<<<cgrid, 256, 0, h->stream>>>(ca);
     commit_cluster_decide<<<cgrid, 256, 0, h->stream>>>(ca);
-    h->kernel_launches += 3;
+    h->kernel_launches += 2;
   } else {
     const uint32_t kgrid = grid_for(rc.num_labels, 128);
     const size_t smem_k = rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0;
@@ -893,7 +1004,7 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
       commit_refine_jmin<<<kgrid, 128, 0, h->stream>>>(ca);
       commit_refine_decide<<<cgrid, 256, smem_k, h->stream>>>(ca);
     }
-    h->kernel_launches += 3 + 2 * passes;
+    h->kernel_launches += 2 + 2 * passes;
     if (rc.has_min) {
       commit_refine_ohist<<<cgrid, 256, 0, h->stream>>>(ca);
       commit_refine_ojmin<<<kgrid, 128, 0, h->stream>>>(ca);
@@ -901,21 +1012,38 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
       h->kernel_launches += 3;
     }
     commit_refine_reset<<<grid_for(static_cast<uint64_t>(rc.num_labels) * kLadderLevels, 128), 128, 0, h->stream>>>(ca);
-    h->kernel_launches += 2;
+    h->kernel_launches += 1;
   }
   timed_end(h, ev);
-  ev = timed_begin(h, 6);
-  // apply + activate in one launch; it also zeroes the other proposal counter for the next sub-round
-  const int variant = (rc.mode == 0 ? 0 : 4) + (q.group > 3 ? 3 : q.group);
-  switch (variant) {
-  case 0: commit_apply_activate<0, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-  case 1: commit_apply_activate<0, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-  case 2: commit_apply_activate<0, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-  case 3: commit_apply_activate<0, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-  case 4: commit_apply_activate<1, 4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  case 5: commit_apply_activate<1, 8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  case 6: commit_apply_activate<1, 32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
-  default: commit_apply_activate<1, 256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, rc.num_labels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * 4 : 0, h->stream>>>(ca); break;
+  // push activation (rounds with few movers): BEFORE apply, which rewrites nothing the walk reads
+  if (!h->pull_this || !h->pull_next) {
+    ev = timed_begin(h, kTagPush);
+    switch (q.group) {
+    case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+    case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+    case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+    default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+    }
+    timed_end(h, ev);
+    ++h->kernel_launches;
+  }
+  ev = timed_begin(h, kTagApply);
+  {
+    const size_t smem_k = (rc.mode == 1 && rc.num_labels <= kSmemPrivLimit) ? static_cast<size_t>(rc.num_labels) * 4 : 0;
+    const uint32_t agrid = grid_for(size, 256, kSMs * 4);
+    if (rc.mode == 0) {
+      if (h->p64) {
+        commit_apply<0, true><<<agrid, 256, 0, h->stream>>>(ca);
+      } else {
+        commit_apply<0, false><<<agrid, 256, 0, h->stream>>>(ca);
+      }
+    } else {
+      if (h->p64) {
+        commit_apply<1, true><<<agrid, 256, smem_k, h->stream>>>(ca);
+      } else {
+        commit_apply<1, false><<<agrid, 256, smem_k, h->stream>>>(ca);
+      }
+    }
   }
   timed_end(h, ev);
   h->kernel_launches += 1;
@@ -924,14 +1052,68 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
   return KMP_OK;
 }
 
+// Activation mode of LP round `iter` (lp_device.cuh): in PULL rounds the sweeps scan every listed vertex
+// and read the moves of their neighbours from the stamps next to the labels -- free when most vertices
+// are active anyway (all of a fresh clustering, the first rounds of a refinement); in PUSH rounds movers
+// flag their neighbours (a second walk over their adjacency) and the sweeps skip inactive vertices
+// without touching their adjacency -- cheaper once few vertices move. Round r + 1 pulls iff at least
+// 1/16 of the listed vertices moved in round r - 1 (rounds 0 and 1 always pull); movers push whenever the
+// running or the next round reads flags. Both modes give the same active set as the reference's flags.
+void choose_activation(kmp_lp_handle *h, uint32_t iter) {
+  // a capped neighbourhood scan cannot see all neighbours' stamps
+  const bool can_pull = h->stamps_ok && h->cfg.max_num_neighbors >= h->max_degree;
+  auto heavy = [&](uint32_t moved) { return moved == 0xFFFFFFFFu || 16ull * moved >= h->visited_total; };
+  if (iter == 0) {
+    h->moved_hist[0] = h->moved_hist[1] = 0xFFFFFFFFu; // [0]: round iter - 1, [1]: round iter - 2
+    h->pull_this = can_pull;
+  } else {
+    h->pull_this = h->pull_next;
+  }
+  h->pull_next = can_pull && heavy(h->moved_hist[0]);
+  if (const char *e = std::getenv("KMP_ACTIVATION")) { // experiments / tests: force one mode
+    if (e[0] == 'p' && e[1] == 'u' && e[2] == 's') {
+      h->pull_this = h->pull_next = false;
+    } else if (e[0] == 'p' && e[1] == 'u' && e[2] == 'l' && can_pull) {
+      h->pull_this = h->pull_next = true;
+    }
+  }
+}
+
+int begin_iteration(kmp_lp_handle *h, uint32_t iter) {
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
+  KMP_CUDA(cudaMemsetAsync(h->queue.p, 0, h->queue.cap * sizeof(uint32_t), h->stream));
+  h->mover_parity = 0;
+  choose_activation(h, iter);
+  h->pull_rounds += h->pull_this ? 1 : 0;
+  h->push_rounds += (!h->pull_this || !h->pull_next) ? 1 : 0;
+  if (iter >= 2 && h->stamps_ok && h->n > 0) {
+    const int ev = timed_begin(h, kTagMisc);
+    if (h->p64) {
+      k_age_stamps<true><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->labg.p, iter & 1u);
+    } else {
+      k_age_stamps<false><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->labg.p, iter & 1u);
+    }
+    timed_end(h, ev);
+    ++h->kernel_launches;
+  }
+  return KMP_OK;
+}
+
+void end_iteration(kmp_lp_handle *h, uint32_t moved) {
+  h->moved_hist[1] = h->moved_hist[0];
+  h->moved_hist[0] = moved;
+}
+
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
 int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
   const uint32_t S = h->lists_S;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
-  h->mover_parity = 0;
+  int rc0 = begin_iteration(h, iter);
+  if (rc0 != KMP_OK) {
+    return rc0;
+  }
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
     const SubRound q = subround_of_sg(h, sg);
-    if (q.size_a + q.size_b == 0) {
+    if (q.total == 0) {
       continue;
     }
     int rc2 = sweep_subround(h, rc, iter, sg, q);
@@ -947,8 +1129,32 @@ int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *m
   KMP_CUDA(cudaMemcpyAsync(host, h->ctr32.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *moved = host[1];
+  end_iteration(h, host[1]);
   (void)proposals;
   return KMP_OK;
+}
+
+// packed gather array: word width by the label range; (re)allocated grow-only
+int prepare_labg(kmp_lp_handle *h, uint32_t num_labels) {
+  h->p64 = num_labels > (1u << 24);
+  KMP_CUDA(h->labg.ensure(static_cast<size_t>(std::max<uint32_t>(h->n, 1)) * (h->p64 ? 8 : 4)));
+  return KMP_OK;
+}
+void launch_init_cluster(kmp_lp_handle *h) {
+  if (h->p64) {
+    k_init_cluster<true><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->vwgt, h->label.p, h->labg.p, h->weight.p,
+                                                                       h->favored.p, h->active.p);
+  } else {
+    k_init_cluster<false><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->vwgt, h->label.p, h->labg.p, h->weight.p,
+                                                                        h->favored.p, h->active.p);
+  }
+}
+void launch_pack_labels(kmp_lp_handle *h) {
+  if (h->p64) {
+    k_pack_labels<true><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->label.p, h->labg.p);
+  } else {
+    k_pack_labels<false><<<grid_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->label.p, h->labg.p);
+  }
 }
 
 int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
@@ -961,6 +1167,7 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   }
   h->kernel_launches = 0;
   h->sweep_launches = 0;
+  h->pull_rounds = h->push_rounds = 0;
   h->sweep_events_used = 0;
   for (int g = 0; g < 8; ++g) {
     h->group_launches[g] = 0;
@@ -993,10 +1200,13 @@ int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
         sweep += t;
       }
       stats->group_sweep_ms[h->sweep_event_group[i]] += t;
+      (void)kTagPush;
     }
     stats->sweep_ms = sweep;
     stats->sweep_launches = h->sweep_launches;
     stats->kernel_launches = h->kernel_launches;
+    stats->pull_rounds = h->pull_rounds;
+    stats->push_rounds = h->push_rounds;
   }
   return KMP_OK;
 }
@@ -1120,6 +1330,31 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
                                   cudaGetErrorString(e));
   }
+  // options the sync schedule cannot honour are refused, never silently mapped to something else
+  if (cfg->schedule != KMP_SCHEDULE_SYNC && cfg->schedule != KMP_SCHEDULE_SEQ_STRICT) {
+    return fail(KMP_ERR_INVALID, "unknown schedule");
+  }
+  if (cfg->schedule == KMP_SCHEDULE_SYNC) {
+    if (cfg->tie_breaking_strategy == KMP_TIE_GEOMETRIC) {
+      return fail(KMP_ERR_UNSUPPORTED, "tie_breaking_strategy GEOMETRIC is order-dependent (lp_clusterer.cc:252-278): "
+                                       "use KMP_SCHEDULE_SEQ_STRICT or UNIFORM");
+    }
+    if (cfg->tie_breaking_strategy != KMP_TIE_UNIFORM) {
+      return fail(KMP_ERR_INVALID, "unknown tie_breaking_strategy");
+    }
+    if (cfg->two_hop_strategy == KMP_TWO_HOP_MATCH || cfg->two_hop_strategy == KMP_TWO_HOP_CLUSTER) {
+      return fail(KMP_ERR_UNSUPPORTED, "global two-hop MATCH / CLUSTER (label_propagation.h:1030-1191) is an id-ordered "
+                                       "chain: use the *_THREADWISE variants or KMP_SCHEDULE_SEQ_STRICT");
+    }
+    if (cfg->relabel_before_second_phase != 0) {
+      return fail(KMP_ERR_UNSUPPORTED, "relabel_before_second_phase: the sync schedule has no second phase");
+    }
+  }
+  if (cfg->two_hop_strategy < KMP_TWO_HOP_DISABLE || cfg->two_hop_strategy > KMP_TWO_HOP_CLUSTER_THREADWISE ||
+      cfg->isolated_nodes_strategy < KMP_ISOLATED_KEEP || cfg->isolated_nodes_strategy > KMP_ISOLATED_CLUSTER_DURING_TWO_HOP ||
+      cfg->impl < KMP_LP_SINGLE_PHASE || cfg->impl > KMP_LP_GROWING_HASH_TABLES) {
+    return fail(KMP_ERR_INVALID, "unknown two_hop_strategy / isolated_nodes_strategy / impl");
+  }
   kmp_lp_handle *h = new (std::nothrow) kmp_lp_handle();
   if (h == nullptr) {
     return fail(KMP_ERR_ALLOC, "out of host memory");
@@ -1148,13 +1383,14 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_CUDA, "failed to create stream/events");
   }
   h->stream = h->owned_stream;
-  {
-    const int smem_g = kGroupTableSlots * kGroupsPerBlock * 8;
-    cudaFuncSetAttribute(sweep_group<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-    cudaFuncSetAttribute(sweep_group<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-    cudaFuncSetAttribute(sweep_group<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-    cudaFuncSetAttribute(sweep_group<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g);
-  }
+  configure_team_kernels<0, false, false>();
+  configure_team_kernels<0, false, true>();
+  configure_team_kernels<0, true, false>();
+  configure_team_kernels<0, true, true>();
+  configure_team_kernels<1, false, false>();
+  configure_team_kernels<1, false, true>();
+  configure_team_kernels<1, true, false>();
+  configure_team_kernels<1, true, true>();
   *out = h;
   return KMP_OK;
 }
@@ -1270,14 +1506,17 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   if (rc != KMP_OK) {
     return rc;
   }
+  rc = prepare_labg(h, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
   rc = upload_optional_u32(h, h->communities, communities, n);
   if (rc != KMP_OK) {
     return rc;
   }
   KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   if (n > 0) {
-    k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p,
-                                                            h->active.p);
+    launch_init_cluster(h);
     ++h->kernel_launches;
   }
   RunCtx ctx{0, n, max_cluster_weight, false, communities != nullptr};
@@ -1371,6 +1610,10 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (rc != KMP_OK) {
     return rc;
   }
+  rc = prepare_labg(h, k);
+  if (rc != KMP_OK) {
+    return rc;
+  }
   if (partition_inout != nullptr && n > 0) {
     KMP_CUDA(cudaMemcpyAsync(h->label.p, partition_inout, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
   }
@@ -1388,7 +1631,8 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (n > 0) {
     k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
     k_fill_u8<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->active.p, 1); // Base::initialize: all active
-    h->kernel_launches += 2;
+    launch_pack_labels(h);
+    h->kernel_launches += 3;
   }
   RunCtx ctx{1, k, 0, min_block_weights != nullptr, communities != nullptr};
   const uint64_t max_it = h->cfg.num_iterations == 0 ? ~0ull : h->cfg.num_iterations; // lp_refiner.cc:78-79
@@ -1436,6 +1680,10 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   if (rc != KMP_OK) {
     return rc;
   }
+  rc = prepare_labg(h, mode == 0 ? std::max(n, num_labels) : num_labels);
+  if (rc != KMP_OK) {
+    return rc;
+  }
   DevBuf<uint32_t> d_target, d_fav;
   KMP_CUDA(d_target.ensure(n));
   KMP_CUDA(d_fav.ensure(n));
@@ -1452,30 +1700,34 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
     }
   }
   KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  if (n > 0) {
+    launch_pack_labels(h);
+  }
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // hub work-queue cursors
+  KMP_CUDA(cudaMemsetAsync(h->queue.p, 0, h->queue.cap * sizeof(uint32_t), h->stream));
   sa.sel_target = d_target.p;
   sa.sel_favored = mode == 0 ? d_fav.p : nullptr;
   sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
   sa.base_fav = sync_base(h->cfg.seed, call_index, iteration, SALT_FAV);
   const uint32_t S = h->lists_S;
-  for (uint32_t sg = 0; sg < kNumTiers * S; ++sg) {
-    const uint32_t off = h->list_off[sg];
-    const uint32_t size = h->list_off[sg + 1] - off;
+  for (uint32_t ts = 0; ts < kNumTiers * S; ++ts) { // every (tier, class) list once
+    const uint32_t off = h->list_off[ts];
+    const uint32_t size = h->list_off[ts + 1] - off;
+    const int tier = static_cast<int>(ts / S);
     sa.list = h->order.p + off;
     sa.list_size = size;
-    h->cur_subround = sg % S;
-    KMP_CUDA(launch_sweep(h, mode, static_cast<int>(sg / S), sa));
+    h->cur_subround = ts % S;
+    h->cur_sg = group_of_tier(tier) * S + ts % S; // one queue cursor per (tier, sub-round)
+    KMP_CUDA(launch_sweep(h, mode, tier, sa));
   }
   KMP_CUDA(cudaMemcpyAsync(target_out, d_target.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
   if (favored_out != nullptr) {
     KMP_CUDA(cudaMemcpyAsync(favored_out, d_fav.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
   }
   KMP_CUDA(cudaStreamSynchronize(h->stream));
-  d_target.release();
-  d_fav.release();
   return KMP_OK;
 }
 
@@ -1508,6 +1760,7 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ctr32.release();
   h->ctr64.release();
   h->hub_tab.release();
+  h->labg.release();
   h->cub_tmp.release();
   h->pairs_a.release();
   h->pairs_b.release();
@@ -1583,7 +1836,7 @@ int kmp_lp_subround_cap(kmp_lp_handle *h, uint32_t sg, uint32_t *cap_out, uint32
     *cap_out = subround_cap(h, q);
   }
   if (size_out != nullptr) {
-    *size_out = q.size_a + q.size_b;
+    *size_out = q.total;
   }
   return KMP_OK;
 }
@@ -1609,10 +1862,15 @@ int kmp_lp_step_begin_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, cons
   if (rc != KMP_OK) {
     return rc;
   }
+  rc = prepare_labg(h, n);
+  if (rc != KMP_OK) {
+    return rc;
+  }
   KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   if (n > 0) {
-    k_init_cluster<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p, h->favored.p, h->active.p);
+    launch_init_cluster(h);
   }
+  h->step_iter = 0;
   h->step_mode = 0;
   h->step_labels = n;
   h->step_mcw = max_cluster_weight;
@@ -1654,10 +1912,16 @@ int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_bl
   }
   KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
   KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
+  rc = prepare_labg(h, k);
+  if (rc != KMP_OK) {
+    return rc;
+  }
   if (n > 0) {
     k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
     k_fill_u8<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->active.p, 1);
+    launch_pack_labels(h);
   }
+  h->step_iter = 0;
   h->step_mode = 1;
   h->step_labels = k;
   h->step_mcw = 0;
@@ -1670,9 +1934,7 @@ int kmp_lp_step_begin_iteration(kmp_lp_handle *h) {
   if (h == nullptr || h->step_mode < 0) {
     return fail(KMP_ERR_INVALID, "step_begin_* not called");
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
-  h->mover_parity = 0;
-  return KMP_OK;
+  return begin_iteration(h, h->step_iter);
 }
 
 // Sweep this rank's share of sub-round sg and pack its proposals into d_send (device memory,
@@ -1709,7 +1971,7 @@ int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void 
   const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(static_cast<const uint32_t *>(d_gathered), h->world,
                                                                         cap, h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0));
-  const uint32_t agrid = grid_for(q.size_a + q.size_b, 256, kSMs * 8);
+  const uint32_t agrid = grid_for(q.total, 256, kSMs * 8);
   if (rc.mode == 0) {
     k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
                                                           h->incoming.p, h->hist.p, rc.num_labels);
@@ -1734,6 +1996,8 @@ int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved) {
   KMP_CUDA(cudaMemcpyAsync(host, h->ctr32.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *moved = host[1];
+  end_iteration(h, host[1]);
+  ++h->step_iter;
   return KMP_OK;
 }
 

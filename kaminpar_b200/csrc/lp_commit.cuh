@@ -46,6 +46,9 @@ struct CommitArgs {
   int32_t *__restrict__ ojmin; // [k]
   // results
   uint32_t *__restrict__ moved_count;
+  // packed (label, stamp) gather array of the sweeps (lp_device.cuh) and the stamp of this sub-round
+  void *__restrict__ labg;
+  uint32_t stamp;
 };
 
 __device__ __forceinline__ int32_t node_weight(const CommitArgs &a, uint32_t u) {
@@ -153,10 +156,15 @@ __global__ void commit_refine_decide(const CommitArgs a) {
     const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
     if (static_cast<int>(lvl) >= a.jmin[t]) {
       a.acc[i] = 1;
-      if (priv) {
-        atomicAdd(&s_acc[a.label[u]], node_weight(a, u));
-      } else {
-        atomicAdd(&a.out_delta[a.label[u]], node_weight(a, u));
+      // no credit for departures from a block with a min-weight constraint: commit_refine_othin may
+      // still revoke them, and arrivals accepted on that credit would overshoot the block's maximum
+      const uint32_t from = a.label[u];
+      if (a.min_w == nullptr || a.min_w[from] <= 0) {
+        if (priv) {
+          atomicAdd(&s_acc[from], node_weight(a, u));
+        } else {
+          atomicAdd(&a.out_delta[from], node_weight(a, u));
+        }
       }
     }
   }
@@ -221,66 +229,13 @@ __global__ void commit_refine_reset(const CommitArgs a) {
   }
 }
 
-// ---- apply + activate (both modes) ------------------------------------------------------------
-// A team of LANES threads (4, 8, 32 or the whole 256-thread CTA, by the degree group of the
-// sub-round) handles one proposal: lane 0 applies it (label, weights, commit-scratch clean-up;
-// label_propagation.h:826-834) and, if it was accepted, the team flags the neighbours of the moved
-// vertex as active (label_propagation.h:848-870). Rejected proposals stay active for the next
-// round. Thread 0 of the grid also zeroes the proposal counter of the NEXT sub-round.
-// These kernels do very little work per thread; their run time is the number of DEPENDENT global loads
-// on a thread's path times the DRAM latency (ncu: 96 % of the cycles without an eligible warp, 17 load
-// levels in the first version). Every team therefore handles two proposals at a time and issues its
-// loads level by level -- (vertex, target, verdict) -> (adjacency range, slot owner, old label, weight)
-// -> neighbour ids -- before the first store; a byte store may alias anything, so the compiler would
-// not hoist loads above it by itself.
-constexpr int kActivateBatch = 4;
-template <int LANES>
-__device__ __forceinline__ void load_neighbours(const CommitArgs &a, uint32_t e, uint32_t end,
-                                                uint32_t (&v)[kActivateBatch]) {
-#pragma unroll
-  for (int j = 0; j < kActivateBatch; ++j) {
-    v[j] = e + j * LANES < end ? a.adjncy[e + j * LANES] : kEmpty;
-  }
-}
-__device__ __forceinline__ void flag_neighbours(const CommitArgs &a, const uint32_t (&v)[kActivateBatch]) {
-#pragma unroll
-  for (int j = 0; j < kActivateBatch; ++j) {
-    if (v[j] != kEmpty) {
-      a.active[v[j]] = 1;
-    }
-  }
-}
-// lane 0 of a team: the stores of proposal i (vertex u -> target t, accepted iff acc == 1)
-template <int MODE>
-__device__ __forceinline__ void apply_proposal(const CommitArgs &a, uint32_t i, uint32_t u, uint32_t t, uint8_t acc,
-                                               uint32_t slot_owner, uint32_t from, int32_t w, bool priv,
-                                               int32_t *s_delta, uint32_t &moved) {
-  if (MODE == 0) {
-    a.incoming[t] = 0; // every proposer of t writes the same value
-    if (slot_owner == i) { // slot owner cleans the contended-target scratch
-      int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
-#pragma unroll
-      for (int j = 0; j < kLadderLevels; ++j) {
-        h[j] = 0;
-      }
-      a.slotmap[t] = kEmpty;
-    }
-  }
-  if (acc == 1) {
-    if (priv) {
-      atomicAdd(&s_delta[t], w);
-      atomicSub(&s_delta[from], w);
-    } else {
-      atomicAdd(&a.weight[t], w);
-      atomicSub(&a.weight[from], w);
-    }
-    a.label[u] = t;
-    ++moved;
-  } else {
-    a.active[u] = 1; // rejected proposals retry in the next round
-  }
-}
-template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_apply_activate(const CommitArgs a) {
+// ---- apply (both modes) -----------------------------------------------------------------------
+// One thread per proposal: label, packed (label, stamp) gather word, weights, commit-scratch clean-up
+// (label_propagation.h:826-834). Neighbour activation (label_propagation.h:848-870) is NOT done here: in
+// pull mode the next sweep derives it from the stamp written next to the label (lp_device.cuh); in push
+// mode commit_activate below walks the adjacency of the moved vertices. Rejected proposals stay active
+// for the next round. Thread 0 of the grid also zeroes the proposal counter of the NEXT sub-round.
+template <int MODE, bool P64> __global__ void __launch_bounds__(256) commit_apply(const CommitArgs a) {
   extern __shared__ int32_t s_delta[];
   const bool priv = (MODE == 1) && a.k <= kSmemPrivLimit;
   if (priv) {
@@ -291,72 +246,40 @@ template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_app
   }
   const uint32_t cnt = *a.mover_count;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t sub = tid % LANES;
-  const uint32_t nteams = (gridDim.x * blockDim.x) / LANES;
   if (tid == 0) {
     *a.next_mover_count = 0;
   }
   uint32_t moved = 0;
-  for (uint32_t i0 = tid / LANES; i0 < cnt; i0 += 2 * nteams) {
-    const uint32_t i1 = i0 + nteams;
-    const bool has1 = i1 < cnt;
-    // level 1: the two proposals
-    const uint32_t u0 = a.mv_u[i0];
-    const uint32_t t0 = a.mv_t[i0];
-    const uint8_t acc0 = a.acc[i0];
-    const uint32_t u1 = has1 ? a.mv_u[i1] : 0u;
-    const uint32_t t1 = has1 ? a.mv_t[i1] : 0u;
-    const uint8_t acc1 = has1 ? a.acc[i1] : static_cast<uint8_t>(0);
-    // level 2: adjacency ranges (all lanes); slot owner, old label and weight (lane 0)
-    uint32_t beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
-    if (acc0 == 1) {
-      beg0 = a.xadj[u0];
-      end0 = a.xadj[u0 + 1];
-    }
-    if (acc1 == 1) {
-      beg1 = a.xadj[u1];
-      end1 = a.xadj[u1 + 1];
-    }
-    uint32_t owner0 = kEmpty, owner1 = kEmpty, from0 = 0, from1 = 0;
-    int32_t w0 = 1, w1 = 1;
-    if (sub == 0) {
-      if (MODE == 0) {
-        owner0 = a.slotmap[t0];
-        owner1 = has1 ? a.slotmap[t1] : kEmpty;
-      }
-      if (acc0 == 1) {
-        from0 = a.label[u0];
-        w0 = node_weight(a, u0);
-      }
-      if (acc1 == 1) {
-        from1 = a.label[u1];
-        w1 = node_weight(a, u1);
+  for (uint32_t i = tid; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    const uint8_t acc = a.acc[i];
+    if (MODE == 0) {
+      a.incoming[t] = 0; // every proposer of t writes the same value
+      if (a.slotmap[t] == i) { // slot owner cleans the contended-target scratch
+        int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
+#pragma unroll
+        for (int j = 0; j < kLadderLevels; ++j) {
+          h[j] = 0;
+        }
+        a.slotmap[t] = kEmpty;
       }
     }
-    // level 3: the first batch of neighbour ids of both vertices
-    uint32_t e0 = beg0 + sub, e1 = beg1 + sub;
-    uint32_t v0[kActivateBatch], v1[kActivateBatch];
-    load_neighbours<LANES>(a, e0, end0, v0);
-    load_neighbours<LANES>(a, e1, end1, v1);
-    // stores
-    if (sub == 0) {
-      apply_proposal<MODE>(a, i0, u0, t0, acc0, owner0, from0, w0, priv, s_delta, moved);
-      if (has1) {
-        apply_proposal<MODE>(a, i1, u1, t1, acc1, owner1, from1, w1, priv, s_delta, moved);
+    if (acc == 1) {
+      const uint32_t from = a.label[u];
+      const int32_t w = node_weight(a, u);
+      if (priv) {
+        atomicAdd(&s_delta[t], w);
+        atomicSub(&s_delta[from], w);
+      } else {
+        atomicAdd(&a.weight[t], w);
+        atomicSub(&a.weight[from], w);
       }
-    }
-    flag_neighbours(a, v0);
-    flag_neighbours(a, v1);
-    // remaining neighbours (degree > kActivateBatch * LANES): both vertices advance together
-    e0 += kActivateBatch * LANES;
-    e1 += kActivateBatch * LANES;
-    while (e0 < end0 || e1 < end1) {
-      load_neighbours<LANES>(a, e0, end0, v0);
-      load_neighbours<LANES>(a, e1, end1, v1);
-      flag_neighbours(a, v0);
-      flag_neighbours(a, v1);
-      e0 += kActivateBatch * LANES;
-      e1 += kActivateBatch * LANES;
+      a.label[u] = t;
+      static_cast<typename LabG<P64>::word *>(a.labg)[u] = LabG<P64>::pack(t, a.stamp);
+      ++moved;
+    } else {
+      a.active[u] = 1; // rejected proposals retry in the next round
     }
   }
   if (priv) {
@@ -372,6 +295,36 @@ template <int MODE, int LANES> __global__ void __launch_bounds__(256) commit_app
   }
   if ((threadIdx.x & 31) == 0 && moved != 0) {
     atomicAdd(a.moved_count, moved);
+  }
+}
+
+// ---- push activation (only in rounds with few movers, see kmp_lp.cu choose_activation) ---------
+// A team of LANES threads (by the degree group of the sub-round) flags the neighbours of one accepted
+// mover as active (label_propagation.h:848-870).
+template <int LANES> __global__ void __launch_bounds__(256) commit_activate(const CommitArgs a) {
+  const uint32_t cnt = *a.mover_count;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t sub = tid % LANES;
+  const uint32_t nteams = (gridDim.x * blockDim.x) / LANES;
+  for (uint32_t i = tid / LANES; i < cnt; i += nteams) {
+    if (a.acc[i] != 1) {
+      continue;
+    }
+    const uint32_t u = a.mv_u[i];
+    const uint32_t end = a.xadj[u + 1];
+    for (uint32_t e = a.xadj[u] + sub; e < end; e += LANES * 4) {
+      uint32_t v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = e + j * LANES < end ? a.adjncy[e + j * LANES] : kEmpty;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (v[j] != kEmpty) {
+          a.active[v[j]] = 1;
+        }
+      }
+    }
   }
 }
 // acc[] must start at 0 for the refiner's multi-pass decide; clear it and the counters

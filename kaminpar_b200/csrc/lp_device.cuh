@@ -110,6 +110,49 @@ template <int MODE> __device__ __forceinline__ Cand warp_argmax(unsigned mask, C
   return r;
 }
 
+// ---- packed gather array: neighbour label + "moved" stamp in ONE random access -------------------
+// The sweep reads label[v] for every edge. Packing a stamp of v's last move next to the label lets the
+// sweep derive the reference's active flag ("a neighbour moved since my last visit",
+// label_propagation.h:848-870) from the gather it does anyway, instead of a second pass over the
+// adjacency of every moved vertex that scatters active[v] = 1 (pull instead of push).
+//   P64 = false: 32-bit word, label in bits 0..23 (n <= 2^24), stamp in bits 24..31
+//   P64 = true : 64-bit word, label in bits 0..31, stamp in bits 32..63
+// Stamp = 0: not moved in the current or the previous round; otherwise 1 + (round parity << kStampBits)
+// + sub-round index of the move. A vertex u visited in sub-round q of round r has to see the moves of
+// round r (all of them happened before its visit: sub-rounds < q) and the moves of round r-1 in
+// sub-rounds >= q (after its previous visit). Stamps of round r-2 are cleared at the start of round r.
+constexpr uint32_t kStampBits = 6;   // sub-round index < 64 (4 degree groups x S <= 16 sub-rounds)
+constexpr uint32_t kMaxStampSubrounds = 1u << kStampBits;
+template <bool P64> struct LabG;
+template <> struct LabG<false> {
+  using word = uint32_t;
+  static __host__ __device__ __forceinline__ uint32_t label(word w) { return w & 0x00FFFFFFu; }
+  static __host__ __device__ __forceinline__ uint32_t stamp(word w) { return w >> 24; }
+  static __host__ __device__ __forceinline__ word pack(uint32_t label, uint32_t stamp) { return label | (stamp << 24); }
+};
+template <> struct LabG<true> {
+  using word = unsigned long long;
+  static __host__ __device__ __forceinline__ uint32_t label(word w) { return static_cast<uint32_t>(w); }
+  static __host__ __device__ __forceinline__ uint32_t stamp(word w) { return static_cast<uint32_t>(w >> 32); }
+  static __host__ __device__ __forceinline__ word pack(uint32_t label, uint32_t stamp) {
+    return static_cast<word>(label) | (static_cast<word>(stamp) << 32);
+  }
+};
+__host__ __device__ __forceinline__ uint32_t make_stamp(uint32_t round, uint32_t subround) {
+  return 1u + ((round & 1u) << kStampBits) + subround;
+}
+// window test of the visit in (round parity `par`, sub-round `q`): win_start = ((par ^ 1) << kStampBits) + q,
+// win_len = 2^(kStampBits+1) - q; the codes of the window are cyclically contiguous
+struct StampWindow {
+  uint32_t start, len;
+};
+__host__ __device__ __forceinline__ StampWindow make_window(uint32_t round, uint32_t subround) {
+  return StampWindow{(((round & 1u) ^ 1u) << kStampBits) + subround, (2u << kStampBits) - subround};
+}
+__device__ __forceinline__ bool stamp_hit(uint32_t stamp, const StampWindow &w) {
+  return stamp != 0 && ((stamp - 1u - w.start) & ((2u << kStampBits) - 1u)) < w.len;
+}
+
 // ---- per-vertex context -------------------------------------------------------------------------
 struct SweepArgs {
   // graph
@@ -119,6 +162,10 @@ struct SweepArgs {
   const int32_t *__restrict__ adjwgt; // nullable
   // state
   const uint32_t *__restrict__ label;  // frozen during the sweep
+  const void *__restrict__ labg;       // packed (label, stamp) gather array, LabG<P64>::word[n]
+  StampWindow window;                  // which stamps count as "moved since my last visit"
+  bool pull;                           // derive the active flag from the stamps (else: active[] only)
+  uint32_t *__restrict__ queue;        // work-queue cursor of this launch (team kernels), zeroed per round
   const int32_t *__restrict__ weight;  // cluster weights [n] / block weights [k], frozen
   const int32_t *__restrict__ max_w;   // refiner: per block; clusterer: nullptr
   const int32_t *__restrict__ min_w;   // refiner: nullable

@@ -1,12 +1,14 @@
 // The LP sweep kernels: one kernel family per degree group of the sync schedule.
 //
-//   group 0 (deg 1..7)    sweep_thread : one thread per vertex, neighbour labels in registers
-//   group 1 (deg 8..31)   sweep_warp   : one warp per vertex, duplicates merged with match.any
-//   group 2 (deg 32..255) sweep_warp_hash : one warp per vertex, per-warp shared-memory hash map
-//   tier 3 (deg 256..2047) sweep_group : 128 threads per vertex, 4096-slot shared-memory hash map
-//   tier 4 (deg >= 2048)   sweep_hub_aggregate + sweep_hub_select : edge-parallel; 4096-edge chunks
-//                          are aggregated in shared memory and merged into a global table region
-//   (tiers 3 and 4 together are degree group 3 of the schedule)
+//   tier 0 (deg 1..7)      sweep_thread : one thread per vertex, neighbour labels in registers
+//   tier 1 (deg 8..31)     sweep_warp   : one warp per vertex, duplicates merged with match.any
+//   tier 2 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512-slot shared-memory hash map
+//   tier 3 (deg 256..1023) sweep_team<T=128>  : 128 threads per vertex, 2048 slots
+//   tier 4 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
+//   tier 5 (deg 4096..8191) sweep_team<T=1024>: one 1024-thread CTA per vertex, 16384 slots
+//   tier 6 (deg >= 8192)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
+//                          2048-edge chunks, ratings merged into a global table region per vertex
+//   (tiers 3..6 together are degree group 3 of the schedule)
 //
 // Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
 // rating[label[v]] += w(u,v) over adj(u) (:487-505), clear active[u] (:507-508), select
@@ -48,10 +50,16 @@ __device__ __forceinline__ void block_count_flush(const SweepArgs &a, unsigned l
   }
 }
 
+// ---- neighbour access ---------------------------------------------------------------------------
+template <bool P64>
+__device__ __forceinline__ typename LabG<P64>::word load_labg(const SweepArgs &a, uint32_t v) {
+  return static_cast<const typename LabG<P64>::word *>(a.labg)[v];
+}
+
 // ================================================================================================
-// group 0: thread per vertex, deg <= 7 (also used for any deg <= kMaxDeg)
+// tier 0: thread per vertex, deg <= 7
 // ================================================================================================
-template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
+template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
   constexpr int D = 7;
   unsigned long long edges = 0, nodes = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -63,8 +71,8 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread
     int32_t uw = 1;
     if (i < a.list_size) {
       u = a.list[i];
-      const bool is_active = a.active == nullptr || a.active[u] != 0;
-      if (is_active) {
+      const bool flag = a.active == nullptr || a.active[u] != 0;
+      if (flag || a.pull) {
         const uint32_t beg = a.xadj[u];
         uint32_t deg = a.xadj[u + 1] - beg;
         if (deg > a.max_num_neighbors) {
@@ -73,62 +81,67 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread
         const uint32_t own = a.label[u];
         uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
         const int32_t own_w = a.weight[own];
-        edges += deg;
-        nodes += 1;
-        if (a.active != nullptr) {
-          a.active[u] = 0;
-        }
-        bool skip = false;
-        if (MODE == 1) {
-          const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
-          skip = (own_w - uw) < mn; // lp_refiner.cc:160-162
-        }
         uint32_t keys[D];
         int32_t ws[D];
+        bool hit = false;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
           keys[j] = kEmpty;
           ws[j] = 0;
-          if (!skip && j < static_cast<int>(deg)) {
+          if (j < static_cast<int>(deg)) {
             const uint32_t v = a.adjncy[beg + j];
+            const typename LabG<P64>::word g = load_labg<P64>(a, v);
+            hit = hit || stamp_hit(LabG<P64>::stamp(g), a.window);
             bool ok = true;
             if (MODE == 1 && a.communities != nullptr) {
               ok = a.communities[u] == a.communities[v];
             }
             if (ok) {
-              keys[j] = a.label[v];
+              keys[j] = LabG<P64>::label(g);
               ws[j] = EW ? a.adjwgt[beg + j] : 1;
             }
           }
         }
-        const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
-        Cand best = cand_none(), fav = cand_none();
+        if (flag || hit) {
+          edges += deg;
+          nodes += 1;
+          if (a.active != nullptr && flag) {
+            a.active[u] = 0;
+          }
+          bool skip = false;
+          if (MODE == 1) {
+            const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
+            skip = (own_w - uw) < mn; // lp_refiner.cc:160-162
+          }
+          const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+          Cand best = cand_none(), fav = cand_none();
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-          if (keys[j] != kEmpty) {
-            bool rep = true;
-            int32_t rating = 0;
+          for (int j = 0; j < D; ++j) {
+            if (!skip && keys[j] != kEmpty) {
+              bool rep = true;
+              int32_t rating = 0;
 #pragma unroll
-            for (int q = 0; q < D; ++q) {
-              const bool same = keys[q] == keys[j];
-              rating += same ? ws[q] : 0;
-              if (q < j && same) {
-                rep = false;
+              for (int q = 0; q < D; ++q) {
+                const bool same = keys[q] == keys[j];
+                rating += same ? ws[q] : 0;
+                if (q < j && same) {
+                  rep = false;
+                }
               }
-            }
-            if (rep) {
-              Cand f;
-              const Cand c = eval_candidate<MODE>(a, u, own, uw, own_w, keys[j], rating, store_fav, f);
-              if (cand_better<MODE>(c, best)) {
-                best = c;
-              }
-              if (MODE == 0 && cand_better<0>(f, fav)) {
-                fav = f;
+              if (rep) {
+                Cand f;
+                const Cand c = eval_candidate<MODE>(a, u, own, uw, own_w, keys[j], rating, store_fav, f);
+                if (cand_better<MODE>(c, best)) {
+                  best = c;
+                }
+                if (MODE == 0 && cand_better<0>(f, fav)) {
+                  fav = f;
+                }
               }
             }
           }
+          proposes = finish_vertex<MODE>(a, u, own, store_fav, best, fav, target);
         }
-        proposes = finish_vertex<MODE>(a, u, own, store_fav, best, fav, target);
       }
     }
     const unsigned ballot = __ballot_sync(kFull, proposes);
@@ -148,9 +161,9 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_thread
 }
 
 // ================================================================================================
-// group 1: warp per vertex, deg <= 32, duplicates merged by match.any (no hash table)
+// tier 1: warp per vertex, deg <= 32, duplicates merged by match.any (no hash table)
 // ================================================================================================
-template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(const SweepArgs a) {
+template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sweep_warp(const SweepArgs a) {
   // V vertices per warp and loop iteration: all loads of a stage (vertex record; neighbour id; neighbour
   // label) are issued for the V vertices before any of them is consumed, so a warp keeps V dependent
   // load chains in flight instead of one.
@@ -162,15 +175,16 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
   for (uint32_t i0 = warp * V; i0 < a.list_size; i0 += nwarps * V) {
     uint32_t u[V], beg[V], deg[V], own[V];
     int32_t uw[V], own_w[V];
-    bool act[V], skip[V];
+    bool act[V], flag[V], skip[V];
     // stage 1: vertex records (lane q < V loads vertex q, then broadcast)
     {
       uint32_t lu = 0, lbeg = 0, ldeg = 0, lown = 0;
       int32_t luw = 1, lown_w = 0;
-      int lact = 0;
+      int lflag = 0, lvalid = 0;
       if (lane < V && i0 + lane < a.list_size) {
         lu = a.list[i0 + lane];
-        lact = a.active == nullptr ? 1 : static_cast<int>(a.active[lu]);
+        lvalid = 1;
+        lflag = a.active == nullptr ? 1 : static_cast<int>(a.active[lu]);
         lbeg = a.xadj[lu];
         ldeg = a.xadj[lu + 1] - lbeg;
         lown = a.label[lu];
@@ -180,7 +194,8 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
 #pragma unroll
       for (int q = 0; q < V; ++q) {
         u[q] = __shfl_sync(kFull, lu, q);
-        act[q] = __shfl_sync(kFull, lact, q) != 0;
+        flag[q] = __shfl_sync(kFull, lflag, q) != 0;
+        act[q] = __shfl_sync(kFull, lvalid, q) != 0 && (flag[q] || a.pull); // scanned; decided below
         beg[q] = __shfl_sync(kFull, lbeg, q);
         deg[q] = __shfl_sync(kFull, ldeg, q);
         own[q] = __shfl_sync(kFull, lown, q);
@@ -203,7 +218,7 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
     for (int q = 0; q < V; ++q) {
       v[q] = kEmpty;
       w[q] = 0;
-      if (act[q] && !skip[q] && static_cast<uint32_t>(lane) < deg[q]) {
+      if (act[q] && static_cast<uint32_t>(lane) < deg[q]) {
         v[q] = a.adjncy[beg[q] + lane];
         w[q] = EW ? a.adjwgt[beg[q] + lane] : 1;
       }
@@ -211,14 +226,20 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
 #pragma unroll
     for (int q = 0; q < V; ++q) {
       key[q] = kEmpty;
+      bool hit = false;
       if (v[q] != kEmpty) {
-        bool ok = true;
+        const typename LabG<P64>::word g = load_labg<P64>(a, v[q]);
+        hit = stamp_hit(LabG<P64>::stamp(g), a.window);
+        bool ok = !skip[q];
         if (MODE == 1 && a.communities != nullptr) {
-          ok = a.communities[u[q]] == a.communities[v[q]];
+          ok = ok && a.communities[u[q]] == a.communities[v[q]];
         }
         if (ok) {
-          key[q] = a.label[v[q]];
+          key[q] = LabG<P64>::label(g);
         }
+      }
+      if (act[q] && !flag[q]) { // pull: active iff a neighbour moved since the last visit
+        act[q] = __any_sync(kFull, hit);
       }
     }
     // stage 4: ratings by match.any, candidate weights gathered for all V vertices before evaluation
@@ -237,7 +258,7 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
       } else {
         rating[q] = __popc(peers);
       }
-      rep[q] = (key[q] != kEmpty) && (lane == __ffs(peers) - 1);
+      rep[q] = act[q] && (key[q] != kEmpty) && (lane == __ffs(peers) - 1);
       kw[q] = rep[q] ? a.weight[key[q]] : 0;
     }
 #pragma unroll
@@ -258,7 +279,7 @@ template <int MODE, bool EW> __global__ void __launch_bounds__(256) sweep_warp(c
       if (lane == 0) {
         edges += deg[q];
         nodes += 1;
-        if (a.active != nullptr) {
+        if (a.active != nullptr && flag[q]) {
           a.active[u[q]] = 0;
         }
         uint32_t target;
@@ -279,7 +300,7 @@ __device__ __forceinline__ uint32_t pow2_ceil(uint32_t x) { // x >= 1
   return x <= 1 ? 1u : (1u << (32 - __clz(static_cast<int>(x - 1))));
 }
 
-// open addressing, linear probing; keys/vals may point to shared or global memory
+// open addressing, linear probing in shared memory
 __device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_t mask, bool direct, uint32_t key,
                                           int32_t w) {
   uint32_t slot = direct ? key : (lowbias32(key) & mask);
@@ -341,183 +362,104 @@ __device__ __forceinline__ void table64_add_batch(unsigned long long *tab, uint3
 }
 
 // ================================================================================================
-// group 2: warp per vertex, per-warp shared-memory hash map (deg <= 256)
+// tiers 2..5: a TEAM of T threads (one warp, 128, 512 or 1024 threads) per vertex, rating map = an
+// open-addressing table in shared memory sized for the tier's largest degree (load <= 0.5).
+//
+//   1. gather : every thread loads its neighbours (coalesced adjncy stream), gathers the packed
+//               (label, stamp) word of each -- B independent gathers in flight per thread -- and inserts the
+//               label into the table (one shared-memory CAS + one add per edge; the FixedSizeSparseMap role,
+//               kaminpar-common/datastructures/fixed_size_sparse_map.h). The stamps decide whether the vertex
+//               is active at all (pull activation, see lp_device.cuh); an inactive vertex stops here.
+//   2. select : the table is scanned once WITHOUT touching the cluster-weight array: the team arg-max of
+//               (rating, tie hash) over all entries is the favored cluster, and -- if that cluster is feasible,
+//               one broadcast load -- also the move target (lp_clusterer.cc:199-250). Only when the top entry is
+//               infeasible the entries are evaluated in full (one weight gather per distinct label).
+//               The refiner (k blocks, weights cached) always evaluates in full.
+//   3. the scan clears the slots it visited; vertices are claimed from a work queue.
 // ================================================================================================
-constexpr int kWarpTableSlots = 512;
-constexpr int kWarpsPerBlockG2 = 8;
-
-template <int MODE, bool EW>
-__global__ void __launch_bounds__(kWarpsPerBlockG2 * 32) sweep_warp_hash(const SweepArgs a) {
-  __shared__ uint32_t s_keys[kWarpsPerBlockG2][kWarpTableSlots];
-  __shared__ int32_t s_vals[kWarpsPerBlockG2][kWarpTableSlots];
-  unsigned long long edges = 0, nodes = 0;
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  uint32_t *keys = s_keys[wib];
-  int32_t *vals = s_vals[wib];
-  for (int s = lane; s < kWarpTableSlots; s += 32) {
-    keys[s] = kEmpty;
-    vals[s] = 0;
-  }
-  __syncwarp();
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i = warp; i < a.list_size; i += nwarps) {
-    const uint32_t u = a.list[i];
-    if (a.active != nullptr) { // lane 0 reads, so that its later active[u] = 0 cannot split the warp
-      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
-      act = __shfl_sync(kFull, act, 0);
-      if (act == 0) {
-        continue;
-      }
-    }
-    const uint32_t beg = a.xadj[u];
-    uint32_t deg = a.xadj[u + 1] - beg;
-    if (deg > a.max_num_neighbors) {
-      deg = a.max_num_neighbors;
-    }
-    const uint32_t own = a.label[u];
-    const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
-    const int32_t own_w = a.weight[own];
-    if (lane == 0) {
-      edges += deg;
-      nodes += 1;
-      if (a.active != nullptr) {
-        a.active[u] = 0;
-      }
-    }
-    bool skip = false;
-    if (MODE == 1) {
-      const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
-      skip = (own_w - uw) < mn;
-    }
-    const uint32_t distinct = deg < a.num_labels ? deg : a.num_labels;
-    const bool direct = a.num_labels <= static_cast<uint32_t>(kWarpTableSlots);
-    uint32_t cap = direct ? pow2_ceil(a.num_labels) : pow2_ceil(2 * distinct);
-    if (cap < 32) {
-      cap = 32;
-    }
-    const uint32_t mask = cap - 1;
-    if (!skip) {
-      for (uint32_t e0 = 0; e0 < deg; e0 += 32 * 8) {
-        uint32_t kb[8];
-        int32_t wb8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { // up to 8 independent gathers per lane in flight
-          const uint32_t e = e0 + j * 32 + lane;
-          kb[j] = kEmpty;
-          wb8[j] = 0;
-          if (e < deg) {
-            const uint32_t v = a.adjncy[beg + e];
-            bool ok = true;
-            if (MODE == 1 && a.communities != nullptr) {
-              ok = a.communities[u] == a.communities[v];
-            }
-            if (ok) {
-              kb[j] = a.label[v];
-              wb8[j] = EW ? a.adjwgt[beg + e] : 1;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (kb[j] != kEmpty) {
-            table_add(keys, vals, mask, direct, kb[j], wb8[j]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
-    Cand c = cand_none(), f = cand_none();
-    for (uint32_t s0 = 0; s0 < cap; s0 += 32 * 8) {
-      uint32_t kb[8];
-      int32_t rb[8], wb8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t s = s0 + j * 32 + lane;
-        kb[j] = kEmpty;
-        rb[j] = 0;
-        if (s < cap) {
-          kb[j] = keys[s];
-          if (kb[j] != kEmpty) {
-            rb[j] = vals[s];
-            keys[s] = kEmpty;
-            vals[s] = 0;
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        wb8[j] = kb[j] != kEmpty ? a.weight[kb[j]] : 0;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (kb[j] != kEmpty) {
-          Cand ff;
-          const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kb[j], rb[j], wb8[j], store_fav, ff);
-          if (cand_better<MODE>(cc, c)) {
-            c = cc;
-          }
-          if (MODE == 0 && cand_better<0>(ff, f)) {
-            f = ff;
-          }
-        }
-      }
-    }
-    __syncwarp();
-    const Cand best = warp_argmax<MODE>(kFull, c);
-    Cand fav = cand_none();
-    if (MODE == 0 && store_fav) {
-      fav = warp_argmax<0>(kFull, f);
-    }
-    if (lane == 0) {
-      uint32_t target;
-      if (finish_vertex<MODE>(a, u, own, store_fav, best, fav, target)) {
-        const uint32_t idx = atomicAdd(a.mover_count, 1u);
-        emit_proposal<MODE>(a, idx, u, target, uw);
-      }
+template <int T> struct TeamSync {
+  // id: named barrier of the team (1..15); teams of a CTA use distinct ids
+  static __device__ __forceinline__ void sync(int id) {
+    if (T == 32) {
+      __syncwarp();
+    } else {
+      asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(T) : "memory");
     }
   }
-  block_count_flush(a, edges, nodes);
+  static __device__ __forceinline__ bool any(int id, bool p) {
+    if (T == 32) {
+      return __any_sync(kFull, p);
+    } else {
+      int r;
+      asm volatile(
+          "{\n"
+          ".reg .pred q, r;\n"
+          "setp.ne.s32 q, %3, 0;\n"
+          "bar.red.or.pred r, %1, %2, q;\n"
+          "selp.s32 %0, 1, 0, r;\n"
+          "}\n"
+          : "=r"(r)
+          : "r"(id), "r"(T), "r"(static_cast<int>(p))
+          : "memory");
+      return r != 0;
+    }
+  }
+};
+
+// arg-max over a team: warp_argmax, then (T > 32) the warp results through shared memory
+template <int MODE, int T>
+__device__ __forceinline__ Cand team_argmax(int id, int tid, Cand c, Cand *s_red) {
+  Cand r = warp_argmax<MODE>(kFull, c);
+  if (T == 32) {
+    return r;
+  }
+  TeamSync<T>::sync(id); // s_red free (previous use consumed)
+  if ((tid & 31) == 0) {
+    s_red[tid >> 5] = r;
+  }
+  TeamSync<T>::sync(id);
+  Cand x = cand_none();
+  if ((tid & 31) < T / 32) {
+    x = s_red[tid & 31];
+  }
+  return warp_argmax<MODE>(kFull, x);
 }
 
-// ================================================================================================
-// tier 3 (256 <= deg < 2048): 128 threads per vertex, 4096-slot shared-memory hash map per group
-// ================================================================================================
-constexpr int kGroupThreads = 128;
-constexpr int kGroupsPerBlock = 2;
-constexpr int kGroupTableSlots = 4096;
-constexpr uint32_t kTier4MinDegree = 2048;
-
-__device__ __forceinline__ void group_barrier(int id) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kGroupThreads) : "memory");
-}
-
-template <int MODE, bool EW>
-__global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(const SweepArgs a) {
+template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS>
+__global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
+  static_assert((SLOTS & (SLOTS - 1)) == 0, "table size must be a power of two");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ Cand s_best[kGroupsPerBlock][kGroupThreads / 32];
-  __shared__ Cand s_fav[kGroupsPerBlock][kGroupThreads / 32];
-  const int grp = threadIdx.x / kGroupThreads;
-  const int tid = threadIdx.x % kGroupThreads;
-  const int lane = tid & 31;
-  const int wig = tid >> 5;
-  uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw) + grp * kGroupTableSlots;
-  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kGroupTableSlots * kGroupsPerBlock) +
-                  grp * kGroupTableSlots;
-  for (int s = tid; s < kGroupTableSlots; s += kGroupThreads) {
+  __shared__ Cand s_red_all[TEAMS][T > 32 ? T / 32 : 1];
+  __shared__ uint32_t s_next[TEAMS];
+  const int team = threadIdx.x / T;
+  const int tid = threadIdx.x % T;
+  const int bar = 1 + team;
+  uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(team) * SLOTS;
+  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * SLOTS * TEAMS) + static_cast<size_t>(team) * SLOTS;
+  Cand *s_red = s_red_all[team];
+  for (int s = tid; s < SLOTS; s += T) {
     keys[s] = kEmpty;
     vals[s] = 0;
   }
-  group_barrier(1 + grp);
   unsigned long long edges = 0, nodes = 0;
-  const uint32_t gid = blockIdx.x * kGroupsPerBlock + grp;
-  const uint32_t ngroups = gridDim.x * kGroupsPerBlock;
-  for (uint32_t i = gid; i < a.list_size; i += ngroups) {
+  // work queue: the next list index is claimed one vertex ahead
+  if (tid == 0) {
+    s_next[team] = atomicAdd(a.queue, 1u);
+  }
+  TeamSync<T>::sync(bar);
+  while (true) {
+    const uint32_t i = s_next[team];
+    TeamSync<T>::sync(bar); // everybody has read s_next
+    if (i >= a.list_size) {
+      break;
+    }
+    if (tid == 0) {
+      s_next[team] = atomicAdd(a.queue, 1u);
+    }
     const uint32_t u = a.list[i];
-    const bool act = a.active == nullptr || a.active[u] != 0; // uniform: written only after barriers
-    if (!act) {
+    const bool flag = a.active == nullptr || a.active[u] != 0;
+    if (!flag && !a.pull) {
+      TeamSync<T>::sync(bar);
       continue;
     }
     const uint32_t beg = a.xadj[u];
@@ -531,103 +473,141 @@ __global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(co
     bool skip = false;
     if (MODE == 1) {
       const int32_t mn = a.min_w != nullptr ? a.min_w[own] : 0;
-      skip = (own_w - uw) < mn;
+      skip = (own_w - uw) < mn; // lp_refiner.cc:160-162
     }
     const uint32_t distinct = deg < a.num_labels ? deg : a.num_labels;
-    const bool direct = a.num_labels <= static_cast<uint32_t>(kGroupTableSlots);
+    const bool direct = a.num_labels <= static_cast<uint32_t>(SLOTS);
     uint32_t cap = direct ? pow2_ceil(a.num_labels) : pow2_ceil(2 * distinct);
     if (cap < 32) {
       cap = 32;
     }
     const uint32_t mask = cap - 1;
-    if (!skip) {
-      for (uint32_t e0 = 0; e0 < deg; e0 += kGroupThreads * 4) {
-        uint32_t k4[4];
-        int32_t w4[4];
+    // ---- 1. gather + insert --------------------------------------------------------------------
+    bool hit = false;
+    constexpr int B = 4;
+    for (uint32_t e0 = 0; e0 < deg; e0 += T * B) {
+      uint32_t kb[B];
+      int32_t wb[B];
+      uint32_t vb[B];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { // four independent gathers in flight per thread
-          const uint32_t e = e0 + j * kGroupThreads + tid;
-          k4[j] = kEmpty;
-          w4[j] = 0;
-          if (e < deg) {
-            const uint32_t v = a.adjncy[beg + e];
-            bool ok = true;
-            if (MODE == 1 && a.communities != nullptr) {
-              ok = a.communities[u] == a.communities[v];
-            }
-            if (ok) {
-              k4[j] = a.label[v];
-              w4[j] = EW ? a.adjwgt[beg + e] : 1;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (k4[j] != kEmpty) {
-            table_add(keys, vals, mask, direct, k4[j], w4[j]);
-          }
-        }
+      for (int j = 0; j < B; ++j) {
+        const uint32_t e = e0 + j * T + tid;
+        vb[j] = e < deg ? a.adjncy[beg + e] : kEmpty;
+        wb[j] = (EW && e < deg) ? a.adjwgt[beg + e] : 1;
       }
-    }
-    group_barrier(1 + grp);
-    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
-    Cand c = cand_none(), f = cand_none();
-    for (uint32_t s0 = 0; s0 < cap; s0 += kGroupThreads * 8) {
-      uint32_t kb[8];
-      int32_t rb[8], wb8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { // stage 1: shared-memory slots, then the weight gathers in one batch
-        const uint32_t s = s0 + j * kGroupThreads + tid;
+      for (int j = 0; j < B; ++j) {
         kb[j] = kEmpty;
-        rb[j] = 0;
-        if (s < cap) {
-          kb[j] = keys[s];
-          if (kb[j] != kEmpty) {
-            rb[j] = vals[s];
-            keys[s] = kEmpty;
-            vals[s] = 0;
+        if (vb[j] != kEmpty) {
+          const typename LabG<P64>::word g = load_labg<P64>(a, vb[j]);
+          hit = hit || stamp_hit(LabG<P64>::stamp(g), a.window);
+          bool ok = !skip;
+          if (MODE == 1 && a.communities != nullptr) {
+            ok = ok && a.communities[u] == a.communities[vb[j]];
+          }
+          if (ok) {
+            kb[j] = LabG<P64>::label(g);
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        wb8[j] = kb[j] != kEmpty ? a.weight[kb[j]] : 0;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < B; ++j) {
         if (kb[j] != kEmpty) {
-          Cand ff;
-          const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kb[j], rb[j], wb8[j], store_fav, ff);
-          if (cand_better<MODE>(cc, c)) {
-            c = cc;
-          }
-          if (MODE == 0 && cand_better<0>(ff, f)) {
-            f = ff;
-          }
+          table_add(keys, vals, mask, direct, kb[j], wb[j]);
         }
       }
     }
-    const Cand wb = warp_argmax<MODE>(kFull, c);
-    const Cand wf = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
-    if (lane == 0) {
-      s_best[grp][wig] = wb;
-      s_fav[grp][wig] = wf;
-    }
-    group_barrier(1 + grp);
-    if (tid == 0) {
-      Cand best = cand_none(), fav = cand_none();
+    const bool any_hit = TeamSync<T>::any(bar, hit); // also the barrier after the inserts
+    const bool act = flag || any_hit;
+    // ---- 2. select ---------------------------------------------------------------------------------
+    const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+    Cand best = cand_none(), fav = cand_none();
+    if (act) {
+      Cand c = cand_none(), f = cand_none();
+      if (MODE == 0) {
+        // pass A: no weight gathers
+        for (uint32_t s = tid; s < cap; s += T) {
+          const uint32_t k = keys[s];
+          if (k != kEmpty) {
+            const int32_t r = vals[s];
+            Cand x{r, 0, tie_hash(a.base_tie, u, k), k};
+            if (cand_better<0>(x, c)) {
+              c = x;
+            }
+            if (store_fav) {
+              Cand y{r, 0, tie_hash(a.base_fav, u, k), k};
+              if (cand_better<0>(y, f)) {
+                f = y;
+              }
+            }
+          }
+        }
+        const Cand top = team_argmax<0, T>(bar, tid, c, s_red);
+        if (store_fav) {
+          fav = team_argmax<0, T>(bar, tid, f, s_red);
+        }
+        bool top_ok = true;
+        if (top.gain > 0) {
+          top_ok = (a.weight[top.key] + uw <= a.max_cluster_weight) || (top.key == own);
+          if (a.communities != nullptr) {
+            top_ok = top_ok && (a.communities[top.key] == a.communities[own]);
+          }
+        }
+        if (top_ok) {
+          best = top;
+        } else {
+          // pass B: the top entry is full -- evaluate every entry with its cluster weight
+          Cand cb = cand_none();
+          for (uint32_t s0 = 0; s0 < cap; s0 += T * 4) {
+            uint32_t kk[4];
+            int32_t rr[4], ww[4];
 #pragma unroll
-      for (int q = 0; q < kGroupThreads / 32; ++q) {
-        if (cand_better<MODE>(s_best[grp][q], best)) {
-          best = s_best[grp][q];
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t s = s0 + j * T + tid;
+              kk[j] = s < cap ? keys[s] : kEmpty;
+              rr[j] = kk[j] != kEmpty ? vals[s] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ww[j] = kk[j] != kEmpty ? a.weight[kk[j]] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (kk[j] != kEmpty) {
+                Cand ff;
+                const Cand cc = eval_candidate_w<0>(a, u, own, uw, own_w, kk[j], rr[j], ww[j], false, ff);
+                if (cand_better<0>(cc, cb)) {
+                  cb = cc;
+                }
+              }
+            }
+          }
+          best = team_argmax<0, T>(bar, tid, cb, s_red);
         }
-        if (MODE == 0 && cand_better<0>(s_fav[grp][q], fav)) {
-          fav = s_fav[grp][q];
+      } else {
+        for (uint32_t s = tid; s < cap; s += T) {
+          const uint32_t k = keys[s];
+          if (k != kEmpty) {
+            Cand ff;
+            const Cand cc = eval_candidate_w<1>(a, u, own, uw, own_w, k, vals[s], a.weight[k], false, ff);
+            if (cand_better<1>(cc, c)) {
+              c = cc;
+            }
+          }
         }
+        best = team_argmax<1, T>(bar, tid, c, s_red);
       }
+    }
+    // ---- 3. clear the table, finish the vertex ---------------------------------------------------
+    TeamSync<T>::sync(bar); // all scans done before the slots are cleared
+    for (uint32_t s = tid; s < cap; s += T) {
+      keys[s] = kEmpty;
+      vals[s] = 0;
+    }
+    if (act && tid == 0) {
       edges += deg;
       nodes += 1;
-      if (a.active != nullptr) {
+      if (a.active != nullptr && flag) {
         a.active[u] = 0;
       }
       uint32_t target;
@@ -636,13 +616,13 @@ __global__ void __launch_bounds__(kGroupThreads *kGroupsPerBlock) sweep_group(co
         emit_proposal<MODE>(a, idx, u, target, uw);
       }
     }
-    group_barrier(1 + grp); // table reset and s_best consumed before the next vertex
+    TeamSync<T>::sync(bar); // table clean, s_next written
   }
   block_count_flush(a, edges, nodes);
 }
 
 // ================================================================================================
-// tier 4 (deg >= 2048): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
+// tier 6 (deg >= 8192): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
 // shared-memory hash map and merges the distinct keys into the vertex's global table region.
 // Phase 2: one CTA per vertex scans its region, selects, and clears it.
 // ================================================================================================
@@ -669,6 +649,7 @@ struct HubArgs {
   uint32_t rank, world;                   // hub entry i is owned by rank i % world
   uint32_t cap_pct;                       // table slots per 100 distinct labels (hub_cap)
   uint32_t *__restrict__ queue;           // work-queue cursor of this launch (zeroed per LP round)
+  uint32_t *__restrict__ hit;             // per list entry: a neighbour moved since the last visit (pull); reset by final
 };
 constexpr uint32_t kSelPieceSlots = 8192;
 
@@ -729,7 +710,7 @@ constexpr int kHubStages = 3;
 constexpr int kHubConsumerWarps = kChunkThreads / 32;          // 8 consumer warps
 constexpr int kHubThreads = kChunkThreads + 32;                // + 1 producer warp
 
-template <int MODE, bool EW>
+template <int MODE, bool EW, bool P64>
 __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
   // Phase 1 of tier 4, warp-specialised producer / consumer pipeline (3 stages):
   //   producer warp : evaluates the next work item (2048-edge chunk of a hub's adjacency), publishes
@@ -777,7 +758,7 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
         const uint32_t beg0 = hb.item_beg[it];
         const uint32_t full_deg = hb.item_deg[it];
         const uint32_t chunk = hb.item_chunk[it];
-        if (entry % hb.world == hb.rank && (a.active == nullptr || a.active[u] != 0)) {
+        if (entry % hb.world == hb.rank && (a.active == nullptr || a.pull || a.active[u] != 0)) {
           uint32_t deg = full_deg;
           if (deg > a.max_num_neighbors) {
             deg = a.max_num_neighbors;
@@ -834,6 +815,7 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
       const bool gdirect = a.num_labels <= gcap;
       unsigned long long *gt = hb.g_tab + hb.table_off[d.entry];
       const uint32_t staged_end = d.a0 + d.staged;
+      bool hit = false;
       for (uint32_t e0 = d.gbeg + wib * 128; e0 < d.gend; e0 += kHubConsumerWarps * 128) {
         uint32_t k4[4];
         int32_t w4[4];
@@ -848,8 +830,10 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
             if (MODE == 1 && a.communities != nullptr) {
               ok = a.communities[d.u] == a.communities[v];
             }
+            const typename LabG<P64>::word g = load_labg<P64>(a, v);
+            hit = hit || stamp_hit(LabG<P64>::stamp(g), a.window);
             if (ok) {
-              k4[j] = a.label[v];
+              k4[j] = LabG<P64>::label(g);
               w4[j] = EW ? a.adjwgt[e] : 1;
             }
           }
@@ -876,6 +860,9 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
         }
         table64_add_batch<4>(gt, gcap, gdirect, k4, w4);
       }
+      if (a.pull && __any_sync(kFull, hit) && lane == 0) {
+        atomicOr(&hb.hit[d.entry], 1u);
+      }
     }
     __syncwarp();
     if (lane == 0) {
@@ -895,7 +882,8 @@ template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_p
     const uint32_t entry = hb.sel_entry[it];
     const uint32_t u = a.list[entry];
     Cand c = cand_none(), f = cand_none();
-    const bool act = (entry % hb.world == hb.rank) && (a.active == nullptr || a.active[u] != 0);
+    // the region is scanned (and cleaned) whenever it was aggregated; activity is decided by sweep_hub_final
+    const bool act = (entry % hb.world == hb.rank) && (a.active == nullptr || a.pull || a.active[u] != 0);
     if (act) {
       const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
       const uint32_t own = a.label[u];
@@ -973,10 +961,20 @@ template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const
       continue;
     }
     const uint32_t u = a.list[i];
+    bool flag = true;
     if (a.active != nullptr) {
-      int act = (lane == 0) ? static_cast<int>(a.active[u]) : 0;
-      act = __shfl_sync(kFull, act, 0);
-      if (act == 0) {
+      int fl = 0, ht = 0;
+      if (lane == 0) {
+        fl = static_cast<int>(a.active[u]);
+        if (a.pull) {
+          ht = static_cast<int>(hb.hit[i]);
+          hb.hit[i] = 0;
+        }
+      }
+      fl = __shfl_sync(kFull, fl, 0);
+      ht = __shfl_sync(kFull, ht, 0);
+      flag = fl != 0;
+      if (fl == 0 && ht == 0) {
         continue;
       }
     }
@@ -1010,7 +1008,7 @@ template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const
     if (lane == 0) {
       edges += deg;
       nodes += 1;
-      if (a.active != nullptr) {
+      if (a.active != nullptr && flag) {
         a.active[u] = 0;
       }
       uint32_t target;

@@ -49,6 +49,7 @@ class KmpConfig(C.Structure):
         ("sync_granule_log2", C.c_uint32),
         ("sync_commit_passes", C.c_uint32),
         ("device", C.c_int32),
+        ("schedule", C.c_int32),
     ]
 
 
@@ -68,7 +69,9 @@ class KmpStats(C.Structure):
         ("group_edges", C.c_uint64 * 8),
         ("group_nodes", C.c_uint64 * 8),
         ("group_launches", C.c_uint64 * 8),
-        ("group_sweep_ms", C.c_float * 8),
+        ("group_sweep_ms", C.c_float * 12),
+        ("pull_rounds", C.c_uint32),
+        ("push_rounds", C.c_uint32),
     ]
 
     def moved_list(self):

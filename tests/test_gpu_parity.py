@@ -184,6 +184,8 @@ def test_t1_refinement_min_block_weights_and_unbalanced_start():
                                  min_block_weights=ctx.partition.min_block_weights())
     assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
     assert (ebw >= ctx.partition.min_block_weights()).all()
+    # a move never pushes a block above its maximum (blocks that start overloaded may only shrink)
+    assert (ebw <= np.maximum(ctx.partition.max_block_weights(), bw0)).all()
 
 
 def test_t1_communities_and_limits():

@@ -3,6 +3,7 @@ executable invariants inside the reference's hot path (valid ids, bl
 sum of node weights, limits respected, cut never increases for the refiner's positive-gain moves
 in the sequential schedule)."""
 import numpy as np
+import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
@@ -42,3 +43,24 @@ def test_refinement_invariants(g, seed, k, sched):
     assert (p < k).all() and np.array_equal(H.block_weights(g, p, k), bw) and (bw <= mbw).all()
     if sched == B.SEQ:  # sequential moves have non-negative gain each
         assert B.oracle_edge_cut(g, p) <= B.oracle_edge_cut(g, part)
+
+
+@pytest.mark.parametrize("name", ["rgg2d_k4", "walshaw_k16", "rmat13_w"])
+def test_sync_refine_with_min_weights_never_overshoots_max(name):
+    """arrivals accepted on the credit of departures that the min-weight thinning later revokes
+    must not push a block above its maximum (the reference's move_block_weight checks both limits atomically,
+    partitioned_graph.h:397-428)."""
+    from tests.helpers import load_case
+
+    g, _ = load_case(name)
+    w = np.ones(g.n, np.int64) if g.vwgt is None else g.vwgt.astype(np.int64)
+    for k in (2, 8):
+        part = (np.arange(g.n) * k // g.n).astype(np.uint32)
+        bw0 = np.bincount(part, weights=w, minlength=k).astype(np.int64)
+        mbw = np.full(k, int(1.01 * bw0.max()) + int(w.max()), np.int32)
+        minw = (0.98 * bw0).astype(np.int32)
+        for passes in (1, 4):
+            rp = B.oracle_params(B.default_refine_params(), commit_passes=passes)
+            ep, ebw = B.oracle_lp_refine(g, 5, k, mbw, part, schedule=B.SYNC, params=rp, min_block_weights=minw)
+            assert np.array_equal(np.bincount(ep, weights=w, minlength=k).astype(np.int64), ebw.astype(np.int64))
+            assert (ebw >= minw).all() and (ebw <= np.maximum(mbw, bw0)).all(), (name, k, passes, ebw, mbw, minw)
