@@ -390,11 +390,13 @@ def main():
     sampler.start()
     tot_ms = 0.0
     edges = nodes = launches = sweeps = 0
-    g_edges = [0] * 5
-    g_nodes = [0] * 5
-    g_ms = [0.0] * 5
-    commit_ms = apply_ms = 0.0
-    g_launch = [0] * 5
+    NT = 7  # kernel tiers (include/kaminpar_b200_lp.h kmp_lp_stats)
+    g_edges = [0] * NT
+    g_nodes = [0] * NT
+    g_ms = [0.0] * NT
+    commit_ms = apply_ms = push_ms = 0.0
+    pull_rounds = push_rounds = 0
+    g_launch = [0] * NT
     last = None
     for _ in range(args.steps):
         st = run_resident()
@@ -403,13 +405,16 @@ def main():
         nodes += st.nodes_visited
         launches += st.kernel_launches
         sweeps += st.sweep_launches
-        for q in range(5):
+        for q in range(NT):
             g_edges[q] += st.group_edges[q]
             g_nodes[q] += st.group_nodes[q]
             g_ms[q] += st.group_sweep_ms[q]
             g_launch[q] += st.group_launches[q]
-        commit_ms += st.group_sweep_ms[5]
-        apply_ms += st.group_sweep_ms[6]
+        commit_ms += st.group_sweep_ms[8]
+        apply_ms += st.group_sweep_ms[9]
+        push_ms += st.group_sweep_ms[10]
+        pull_rounds += st.pull_rounds
+        push_rounds += st.push_rounds
         last = st
     barrier()
     clocks = sampler.stop()
@@ -487,8 +492,8 @@ def main():
 
     # ---- roofline of the dominant sweep kernel family -------------------------------------------
     peak, peak_src = peaks()
-    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_warp_hash(deg<256)", "sweep_group(deg<2048)",
-             "sweep_hub_aggregate+select(deg>=2048)"]
+    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_team<32>(deg<256)", "sweep_team<128>(deg<1024)",
+             "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<8192)", "sweep_hub_aggregate+partial+final(deg>=8192)"]
     dom = int(np.argmax(g_ms))
     alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]
     achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0
@@ -496,7 +501,7 @@ def main():
     sweep_ms_total = sum(g_ms)
     traffic = None
     try:  # DRAM bytes per launch of this kernel from the committed ncu capture (profiles/), if any
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             traffic = json.load(f).get(wl, {}).get(names[dom], {}).get("traffic_bytes_per_launch")
     except Exception:
         traffic = None
@@ -510,7 +515,14 @@ def main():
                        "share_of_step": sweep_ms_total / tot_ms if tot_ms > 0 else None,
                        "per_group_ms": [x / args.steps for x in g_ms],
                        "per_group_edges": [x // args.steps for x in g_edges]},
-        "commit_ms": commit_ms / args.steps, "apply_activate_ms": apply_ms / args.steps,
+        "commit_ms": commit_ms / args.steps, "apply_ms": apply_ms / args.steps, "push_activate_ms": push_ms / args.steps,
+        "pull_rounds_per_step": pull_rounds / args.steps, "push_rounds_per_step": push_rounds / args.steps,
+        "gather_bound": {
+            # scripts/microbench_lsu.cu on this pool's B200: random 4-byte gathers from an L2-resident table
+            # (one per scanned edge is the floor of any LP sweep on a graph without locality) run at 272 G/s
+            "l2_gather_per_s": 272e9,
+            "all_sweeps_frac_of_gather_bound": (edges / (sweep_ms_total * 1e-3) / 272e9) if sweep_ms_total > 0 else None,
+        },
     }
 
     cpu = None

@@ -69,8 +69,8 @@ typedef struct {
                                       KMP_ERR_UNSUPPORTED under SYNC and implemented by SEQ_STRICT */
   double two_hop_threshold;        /* 0.5 */
   int32_t isolated_nodes_strategy; /* clusterer only; all five values */
-  int32_t relabel_before_second_phase; /* must be 0 (the default, presets.cc:147) under SYNC: there is no second
-                                      phase to relabel for; non-zero = KMP_ERR_UNSUPPORTED */
+  int32_t relabel_before_second_phase; /* must be 0 (the default, presets.cc:147); the cluster-id compaction of
+                                      label_propagation.h:272-319 is not implemented: non-zero = KMP_ERR_UNSUPPORTED */
   /* engine */
   int32_t seed;                /* Random::reseed() analogue; enters every hash key */
   uint32_t sync_subrounds;     /* S: hashed sub-rounds per degree group and iteration (8) */
@@ -136,6 +136,12 @@ int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *x
  * caller (must outlive their use by the handle). */
 int kmp_lp_set_graph_device(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *d_xadj,
                             const uint32_t *d_adjncy, const int32_t *d_vwgt, const int32_t *d_adjwgt);
+
+/* CSRGraph::sorted() of the graph just set (csr_graph.h: degree-bucket sorted, as KaMinPar::compute_partition
+ * feeds the finest level, kaminpar.cc:369-396; coarse graphs are unsorted = one bucket, csr_graph.cc:242-245).
+ * Only KMP_SCHEDULE_SEQ_STRICT reads it -- the reference's chunk order depends on the bucket array
+ * (label_propagation.h:1736-1854); set_graph resets it to 0. */
+int kmp_lp_set_graph_sorted(kmp_lp_handle *h, int sorted);
 
 /* LPClustering::set_max_cluster_weight / set_desired_cluster_count / set_communities +
  * compute_clustering. clustering_out: HOST buffer of n NodeIDs (cluster = id of a vertex in

@@ -25,6 +25,7 @@
 #include "../../include/kaminpar_b200_lp.h"
 #include "lp_commit.cuh"
 #include "lp_device.cuh"
+#include "lp_strict.cuh"
 #include "lp_sweep.cuh"
 
 using namespace kmp;
@@ -173,6 +174,15 @@ struct kmp_lp_handle {
   DevBuf<uint32_t> ct_flags, ct_rank, ct_cl;
   DevBuf<unsigned long long> ct_counter;
   bool slot_state_clean = false; // incoming/slotmap/chist zeroed for current n
+
+  // schedule KMP_SCHEDULE_SEQ_STRICT (lp_strict.cuh): sequential engine state
+  bool graph_sorted = false; // CSRGraph::sorted() of the current graph (kmp_lp_set_graph_sorted)
+  bool strict_seeded = false;
+  DevBuf<int32_t> st_slot, st_ent_val, st_slot2, st_ent2_val, st_concurrent;
+  DevBuf<uint32_t> st_ent_key, st_ent2_key, st_used, st_second, st_tie_best, st_tie_fav, st_chunks, st_sub_perm,
+      st_match, st_buckets;
+  DevBuf<kmp_strict::Rng> st_rng;
+  DevBuf<kmp_strict::Stats> st_stats;
 
   uint32_t call_counter = 0;
   uint64_t kernel_launches = 0, sweep_launches = 0;
@@ -1282,6 +1292,174 @@ int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, 
   return KMP_OK;
 }
 
+// ---- schedule KMP_SCHEDULE_SEQ_STRICT ----------------------------------------------------------------
+// mode 0: labels are (re)initialised by the engine; mode 1: h->label holds the partition. Results stay in
+// h->label / h->weight; iteration statistics go to *stats, the scan counters to tier slot 7 of ctr64.
+int run_strict(kmp_lp_handle *h, int mode, uint32_t num_keys, int32_t max_cluster_weight, uint32_t desired,
+               uint32_t k, bool has_min, bool has_comm, kmp_lp_stats *stats) {
+  const size_t n = std::max<uint32_t>(h->n, 1);
+  const size_t keys = std::max<size_t>(std::max<size_t>(num_keys, n), 1);
+  KMP_CUDA(h->favored.ensure(n));
+  KMP_CUDA(h->active.ensure(n));
+  KMP_CUDA(h->st_slot.ensure(keys));
+  KMP_CUDA(h->st_slot2.ensure(keys));
+  KMP_CUDA(h->st_concurrent.ensure(keys));
+  KMP_CUDA(h->st_used.ensure(keys));
+  KMP_CUDA(h->st_ent_key.ensure(keys + 1));
+  KMP_CUDA(h->st_ent_val.ensure(keys + 1));
+  KMP_CUDA(h->st_ent2_key.ensure(keys + 1));
+  KMP_CUDA(h->st_ent2_val.ensure(keys + 1));
+  KMP_CUDA(h->st_tie_best.ensure(keys + 1));
+  KMP_CUDA(h->st_tie_fav.ensure(keys + 1));
+  KMP_CUDA(h->st_second.ensure(n));
+  KMP_CUDA(h->st_chunks.ensure(2 * (n + 64)));
+  KMP_CUDA(h->st_sub_perm.ensure(n / 64 + 2));
+  KMP_CUDA(h->st_match.ensure(n));
+  KMP_CUDA(h->st_buckets.ensure(36));
+  KMP_CUDA(h->st_rng.ensure(1));
+  KMP_CUDA(h->st_stats.ensure(1));
+  if (!h->strict_seeded) { // Random::reseed + the RandomPermutations member of the LP object, once per object
+    kmp_strict::strict_seed_kernel<<<1, 32, 0, h->stream>>>(h->st_rng.p, h->cfg.seed);
+    h->strict_seeded = true;
+    ++h->kernel_launches;
+  }
+  kmp_strict::Args a{};
+  a.n = h->n;
+  a.m = h->m;
+  a.xadj = h->xadj;
+  a.adjncy = h->adjncy;
+  a.vwgt = h->vwgt;
+  a.adjwgt = h->adjwgt;
+  a.sorted = h->graph_sorted ? 1 : 0;
+  a.buckets = h->st_buckets.p;
+  a.num_iterations = h->cfg.num_iterations;
+  a.large_degree_threshold = h->cfg.large_degree_threshold;
+  a.max_num_neighbors = h->cfg.max_num_neighbors;
+  a.impl = h->cfg.impl;
+  a.tie_uniform = h->cfg.tie_breaking_strategy == KMP_TIE_UNIFORM ? 1 : 0;
+  a.two_hop_strategy = h->cfg.two_hop_strategy;
+  a.isolated_nodes_strategy = h->cfg.isolated_nodes_strategy;
+  a.two_hop_threshold = h->cfg.two_hop_threshold;
+  a.mode = mode;
+  a.max_cluster_weight = max_cluster_weight;
+  a.desired_num_clusters = desired;
+  a.k = k;
+  a.max_bw = mode == 1 ? h->maxw.p : nullptr;
+  a.min_bw = has_min ? h->minw.p : nullptr;
+  a.communities = has_comm ? h->communities.p : nullptr;
+  a.label = h->label.p;
+  a.weight = h->weight.p;
+  a.favored = h->favored.p;
+  a.active = h->active.p;
+  a.slot = h->st_slot.p;
+  a.ent_key = h->st_ent_key.p;
+  a.ent_val = h->st_ent_val.p;
+  a.slot2 = h->st_slot2.p;
+  a.ent2_key = h->st_ent2_key.p;
+  a.ent2_val = h->st_ent2_val.p;
+  a.concurrent = h->st_concurrent.p;
+  a.used_entries = h->st_used.p;
+  a.second_phase_nodes = h->st_second.p;
+  a.tie_best = h->st_tie_best.p;
+  a.tie_fav = h->st_tie_fav.p;
+  a.chunks = h->st_chunks.p;
+  a.sub_perm = h->st_sub_perm.p;
+  a.match_map = h->st_match.p;
+  a.rng = h->st_rng.p;
+  a.stats = h->st_stats.p;
+  kmp_strict::strict_kernel<<<1, 32, 0, h->stream>>>(a);
+  ++h->kernel_launches;
+  KMP_CUDA(cudaGetLastError());
+  kmp_strict::Stats hs{};
+  KMP_CUDA(cudaMemcpyAsync(&hs, h->st_stats.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaStreamSynchronize(h->stream));
+  if (stats != nullptr) {
+    stats->iterations = hs.iterations;
+    for (uint32_t i = 0; i < 64; ++i) {
+      stats->moved[i] = hs.moved[i];
+    }
+    stats->num_clusters = hs.num_clusters;
+    stats->two_hop_ran = hs.two_hop_ran;
+  }
+  // end_call sums the per-tier scan counters: park the engine's totals in tier slot 7
+  unsigned long long c[2] = {hs.edges_scanned, hs.nodes_visited};
+  KMP_CUDA(cudaMemcpy(h->ctr64.p + 7, &c[0], 8, cudaMemcpyHostToDevice));
+  KMP_CUDA(cudaMemcpy(h->ctr64.p + 15, &c[1], 8, cudaMemcpyHostToDevice));
+  return KMP_OK;
+}
+
+int end_call(kmp_lp_handle *h, kmp_lp_stats *stats);
+
+int strict_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desired_num_clusters,
+                   const uint32_t *communities, uint32_t *clustering_out, kmp_lp_stats *stats) {
+  const uint32_t n = h->n;
+  KMP_CUDA(h->label.ensure(std::max<uint32_t>(n, 1)));
+  KMP_CUDA(h->weight.ensure(std::max<uint32_t>(n, 1)));
+  KMP_CUDA(h->ctr64.ensure(32));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  if (communities != nullptr) {
+    KMP_CUDA(h->communities.ensure(n));
+    KMP_CUDA(cudaMemcpyAsync(h->communities.p, communities, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = run_strict(h, 0, n, max_cluster_weight, desired_num_clusters, 0, false, communities != nullptr, stats);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  if (clustering_out != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(clustering_out, h->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  ++h->call_counter;
+  const kmp_lp_stats keep = stats != nullptr ? *stats : kmp_lp_stats{};
+  rc = end_call(h, stats);
+  if (stats != nullptr) { // end_call fills the timing / counter fields only
+    stats->iterations = keep.iterations;
+    std::memcpy(stats->moved, keep.moved, sizeof(keep.moved));
+    stats->num_clusters = keep.num_clusters;
+    stats->two_hop_ran = keep.two_hop_ran;
+  }
+  return rc;
+}
+
+int strict_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights, const int32_t *min_block_weights,
+                  const uint32_t *communities, uint32_t *partition_inout, int32_t *block_weights_out,
+                  kmp_lp_stats *stats) {
+  const uint32_t n = h->n;
+  KMP_CUDA(h->label.ensure(std::max<uint32_t>(n, 1)));
+  KMP_CUDA(h->weight.ensure(std::max<uint32_t>(std::max(n, k), 1)));
+  KMP_CUDA(h->maxw.ensure(k));
+  KMP_CUDA(h->ctr64.ensure(32));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  if (partition_inout != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(h->label.p, partition_inout, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  KMP_CUDA(cudaMemcpyAsync(h->maxw.p, max_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  if (min_block_weights != nullptr) {
+    KMP_CUDA(h->minw.ensure(k));
+    KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_block_weights, static_cast<size_t>(k) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (communities != nullptr) {
+    KMP_CUDA(h->communities.ensure(n));
+    KMP_CUDA(cudaMemcpyAsync(h->communities.p, communities, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = run_strict(h, 1, k, 0, 0, k, min_block_weights != nullptr, communities != nullptr, stats);
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  if (partition_inout != nullptr && n > 0) {
+    KMP_CUDA(cudaMemcpyAsync(partition_inout, h->label.p, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (block_weights_out != nullptr) {
+    KMP_CUDA(cudaMemcpyAsync(block_weights_out, h->weight.p, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  const kmp_lp_stats keep = stats != nullptr ? *stats : kmp_lp_stats{};
+  rc = end_call(h, stats);
+  if (stats != nullptr) {
+    stats->iterations = keep.iterations;
+    std::memcpy(stats->moved, keep.moved, sizeof(keep.moved));
+  }
+  return rc;
+}
+
 } // namespace
 
 // ================================================================================================
@@ -1346,9 +1524,9 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
       return fail(KMP_ERR_UNSUPPORTED, "global two-hop MATCH / CLUSTER (label_propagation.h:1030-1191) is an id-ordered "
                                        "chain: use the *_THREADWISE variants or KMP_SCHEDULE_SEQ_STRICT");
     }
-    if (cfg->relabel_before_second_phase != 0) {
-      return fail(KMP_ERR_UNSUPPORTED, "relabel_before_second_phase: the sync schedule has no second phase");
-    }
+  }
+  if (cfg->relabel_before_second_phase != 0) { // default false (presets.cc:147)
+    return fail(KMP_ERR_UNSUPPORTED, "relabel_before_second_phase (label_propagation.h:272-319) is not implemented");
   }
   if (cfg->two_hop_strategy < KMP_TWO_HOP_DISABLE || cfg->two_hop_strategy > KMP_TWO_HOP_CLUSTER_THREADWISE ||
       cfg->isolated_nodes_strategy < KMP_ISOLATED_KEEP || cfg->isolated_nodes_strategy > KMP_ISOLATED_CLUSTER_DURING_TWO_HOP ||
@@ -1432,6 +1610,13 @@ static int set_graph_common(kmp_lp_handle *h, uint32_t n, uint32_t m) {
   h->have_graph = true;
   h->lists_valid = false;
   h->slot_state_clean = false;
+  h->graph_sorted = false;
+  if (h->cfg.schedule == KMP_SCHEDULE_SEQ_STRICT) {
+    if (n > KMP_SEQ_STRICT_MAX_N) {
+      return fail(KMP_ERR_UNSUPPORTED, "KMP_SCHEDULE_SEQ_STRICT is a one-thread-block schedule for n <= KMP_SEQ_STRICT_MAX_N");
+    }
+    return KMP_OK; // no work lists: the engine walks the reference's chunk order
+  }
   int rc = ensure_lists(h);
   if (rc != KMP_OK) {
     return rc;
@@ -1488,11 +1673,22 @@ int kmp_lp_set_graph_device(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint
   return set_graph_common(h, n, m);
 }
 
+int kmp_lp_set_graph_sorted(kmp_lp_handle *h, int sorted) {
+  if (h == nullptr || !h->have_graph) {
+    return fail(KMP_ERR_INVALID, "no graph set");
+  }
+  h->graph_sorted = sorted != 0;
+  return KMP_OK;
+}
+
 int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desired_num_clusters,
                    const uint32_t *communities, uint32_t *clustering_out, kmp_lp_stats *stats) {
   int rc = begin_call(h, stats);
   if (rc != KMP_OK) {
     return rc;
+  }
+  if (h->cfg.schedule == KMP_SCHEDULE_SEQ_STRICT) {
+    return strict_cluster(h, max_cluster_weight, desired_num_clusters, communities, clustering_out, stats);
   }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
@@ -1598,6 +1794,9 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (rc != KMP_OK) {
     return rc;
   }
+  if (h->cfg.schedule == KMP_SCHEDULE_SEQ_STRICT) {
+    return strict_refine(h, k, max_block_weights, min_block_weights, communities, partition_inout, block_weights_out, stats);
+  }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
   if (rc != KMP_OK) {
@@ -1668,6 +1867,9 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   }
   if (labels == nullptr || weights == nullptr || target_out == nullptr || (mode == 1 && max_weights == nullptr)) {
     return fail(KMP_ERR_INVALID, "null argument");
+  }
+  if (h->cfg.schedule != KMP_SCHEDULE_SYNC) {
+    return fail(KMP_ERR_UNSUPPORTED, "kmp_lp_select_all evaluates the sync selection rule");
   }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
@@ -1846,6 +2048,9 @@ int kmp_lp_step_begin_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, cons
   if (rc != KMP_OK) {
     return rc;
   }
+  if (h->cfg.schedule != KMP_SCHEDULE_SYNC) {
+    return fail(KMP_ERR_UNSUPPORTED, "the stepping API drives the sync schedule");
+  }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
   if (rc != KMP_OK) {
@@ -1887,6 +2092,9 @@ int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_bl
   int rc = begin_call(h, nullptr);
   if (rc != KMP_OK) {
     return rc;
+  }
+  if (h->cfg.schedule != KMP_SCHEDULE_SYNC) {
+    return fail(KMP_ERR_UNSUPPORTED, "the stepping API drives the sync schedule");
   }
   const uint32_t n = h->n;
   rc = ensure_lists(h);

@@ -143,6 +143,10 @@ class EngineContext:
     cluster_commit_passes: int = 1
     refine_commit_passes: int = 4
     device: int = -1
+    # "sync": deterministic synchronous sub-rounds (any size, any number of GPUs); "seq_strict": the
+    # reference's own one-thread order and random draws on one thread block -- bit-identical to the
+    # unmodified reference at one thread, small inputs only (include/kaminpar_b200_lp.h KMP_SCHEDULE_*)
+    schedule: str = "sync"
 
 
 @dataclass
@@ -313,6 +317,8 @@ class LPHandle:
     def set_graph(self, g: CSRGraph):
         _check(self._lib.kmp_lp_set_graph(self._h, C.c_uint32(g.n), C.c_uint32(g.m), _ptr(g.xadj), _ptr(g.adjncy),
                                           _ptr(g.vwgt), _ptr(g.adjwgt)))
+        if g.sorted:  # CSRGraph::sorted(): only the seq_strict schedule reads it (the reference's chunk order)
+            _check(self._lib.kmp_lp_set_graph_sorted(self._h, C.c_int(1)))
         self._graph_id = id(g)
         self._n = g.n
 
@@ -380,11 +386,15 @@ class LPHandle:
         _check(self._lib.kmp_lp_free_scratch(self._h))
 
 
+_SCHEDULES = {"sync": 0, "seq_strict": 1}
+
+
 def _cluster_config(lp: LabelPropagationCoarseningContext, eng: EngineContext) -> KmpConfig:
     return KmpConfig(
         lp.num_iterations, lp.large_degree_threshold, lp.max_num_neighbors, lp.impl, lp.tie_breaking_strategy,
         lp.two_hop_strategy, lp.two_hop_threshold, lp.isolated_nodes_strategy, int(lp.relabel_before_second_phase),
         eng.seed, eng.sync_subrounds, eng.sync_granule_log2, eng.cluster_commit_passes, eng.device,
+        _SCHEDULES[eng.schedule],
     )
 
 
@@ -392,6 +402,7 @@ def _refine_config(lp: LabelPropagationRefinementContext, eng: EngineContext) ->
     return KmpConfig(
         lp.num_iterations, lp.large_degree_threshold, lp.max_num_neighbors, lp.impl, lp.tie_breaking_strategy,
         0, 0.5, 0, 0, eng.seed, eng.sync_subrounds, eng.sync_granule_log2, eng.refine_commit_passes, eng.device,
+        _SCHEDULES[eng.schedule],
     )
 
 

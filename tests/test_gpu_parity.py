@@ -32,6 +32,8 @@ def graphs():
     g0 = rmat(15, 16, 7)
     out["rmat15_sorted"] = B.oracle_rearrange(g0)[0]          # hubs up to deg ~ 10^4 (sweep_block)
     out["rmat14_unsorted_w"] = random_weights(rmat(14, 8, 9), 3, max_vwgt=4, max_adjwgt=7)
+    out["rmat16_hubs"] = B.oracle_rearrange(rmat(16, 32, 5))[0]  # vertices in every kernel tier (deg 1 .. > 8192)
+    out["rmat15_hubs_w"] = random_weights(B.oracle_rearrange(rmat(15, 48, 11))[0], 5, max_vwgt=3, max_adjwgt=5)
     out["grid20"] = B.oracle_rearrange(grid3d(20))[0]
     out["rgg_2e15"] = B.oracle_rearrange(rgg2d(1 << 15, 4))[0]
     out["star_hub"] = H.big_star(40000)                        # global-table path (distinct > 4096)
@@ -53,7 +55,8 @@ def get_graph(name):
 
 
 NAMES = ["rgg2d_k4", "walshaw_k16", "walshaw_unsorted", "rmat13_w", "grid12", "road60", "star30000", "rmat15_sorted",
-         "rmat14_unsorted_w", "grid20", "rgg_2e15", "star_hub", "path", "complete", "bipartite", "with_isolated"]
+         "rmat14_unsorted_w", "rmat16_hubs", "rmat15_hubs_w", "grid20", "rgg_2e15", "star_hub", "path", "complete",
+         "bipartite", "with_isolated"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -143,6 +146,57 @@ def test_t1_hub_table_layout_does_not_change_results(name, knobs, monkeypatch):
     clusterer.set_max_cluster_weight(mcw)
     c = clusterer.compute_clustering(g)
     assert np.array_equal(c, B.oracle_lp_cluster(g, 3, mcw, schedule=B.SYNC))
+
+
+@pytest.mark.parametrize("mode", ["push", "pull"])
+@pytest.mark.parametrize("name", ["rmat16_hubs", "rmat15_hubs_w", "grid20", "walshaw_k16", "star_hub"])
+def test_t1_activation_mode_does_not_change_results(name, mode, monkeypatch):
+    """Pull activation (move stamps read with the neighbour labels) and push activation (movers flag their
+    neighbours, label_propagation.h:848-870) are two implementations of the same active set."""
+    monkeypatch.setenv("KMP_ACTIVATION", mode)
+    g = get_graph(name)
+    ctx, mcw = ctx_for(g, 8, seed=6)
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    c = clusterer.compute_clustering(g)
+    expect, st = B.oracle_lp_cluster(g, 6, mcw, schedule=B.SYNC, return_stats=True)
+    assert np.array_equal(c, expect)
+    gs = clusterer.last_stats
+    assert gs.edges_scanned == st[0].edges_scanned and gs.nodes_visited == st[0].nodes_visited
+    assert (gs.pull_rounds == 0) if mode == "push" else (gs.pull_rounds == gs.iterations)
+    k = 8
+    part = np.random.default_rng(3).integers(0, k, g.n).astype(np.uint32)
+    p_graph = lp.PartitionedGraph(g, k, part)
+    refiner = lp.LabelPropagationRefiner(ctx)
+    refiner.initialize(p_graph)
+    refiner.refine(p_graph, ctx.partition)
+    rp = B.oracle_params(B.default_refine_params(), commit_passes=4)
+    ep, ebw = B.oracle_lp_refine(g, 6, k, ctx.partition.max_block_weights(), part, schedule=B.SYNC, params=rp)
+    assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
+
+
+@pytest.mark.parametrize("name", ["rmat16_hubs", "grid20", "rgg_2e15"])
+def test_t1_long_refinement_switches_to_push_activation(name):
+    """Twelve rounds: once few vertices move the engine switches from pull to push activation on its own
+    (kmp_lp.cu choose_activation); results stay the oracle's, round by round."""
+    g = get_graph(name)
+    k = 16
+    ctx, _ = ctx_for(g, k, seed=8)
+    ctx.refinement.lp.num_iterations = 12
+    part = np.random.default_rng(5).integers(0, k, g.n).astype(np.uint32)
+    p_graph = lp.PartitionedGraph(g, k, part)
+    refiner = lp.LabelPropagationRefiner(ctx)
+    refiner.initialize(p_graph)
+    refiner.refine(p_graph, ctx.partition)
+    base = B.default_refine_params()
+    base.num_iterations = 12
+    rp = B.oracle_params(base, commit_passes=4)
+    ep, ebw, st = B.oracle_lp_refine(g, 8, k, ctx.partition.max_block_weights(), part, schedule=B.SYNC, params=rp,
+                                     return_stats=True)
+    assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
+    gs = refiner.last_stats
+    assert gs.moved_list() == list(st.moved[: st.iterations]) and gs.edges_scanned == st.edges_scanned
+    assert gs.pull_rounds >= 2 and gs.pull_rounds + gs.push_rounds >= gs.iterations
 
 
 @pytest.mark.parametrize("name", NAMES)
