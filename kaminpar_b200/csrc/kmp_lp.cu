@@ -51,14 +51,15 @@ int fail(int code, const std::string &msg) {
 constexpr int kNumGroups = 4; // degree groups of the schedule
 constexpr int kNumTiers = 7;  // kernel tiers: group 3 (deg >= 256) is split into four tiers
 constexpr int kHubTier = 6;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
-constexpr uint32_t kHubMinDegree = 8192;
+constexpr uint32_t kHubMinDegree = 8192;       // graphs with edge weights (32-bit ratings in the team tables)
+constexpr uint32_t kHubMinDegreeUnit = 16384;  // unit edge weights: 16-bit ratings, twice the slots
 constexpr int kSMs = 148;
 constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512)
 constexpr int kTagCommit = 8, kTagApply = 9, kTagPush = 10, kTagMisc = 11; // timing slots besides the tiers
 
 // kernel tier of a vertex of degree d >= 1 (tiers 3..6 are degree group 3 of the schedule)
-__host__ __device__ inline uint32_t tier_of(uint32_t d) {
-  return d < 8 ? 0u : d < 32 ? 1u : d < 256 ? 2u : d < 1024 ? 3u : d < 4096 ? 4u : d < kHubMinDegree ? 5u : 6u;
+__host__ __device__ inline uint32_t tier_of(uint32_t d, uint32_t hub_min) {
+  return d < 8 ? 0u : d < 32 ? 1u : d < 256 ? 2u : d < 1024 ? 3u : d < 4096 ? 4u : d < hub_min ? 5u : 6u;
 }
 inline int group_of_tier(int tier) { return tier < 3 ? tier : 3; }
 
@@ -98,6 +99,12 @@ struct kmp_lp_handle {
   int device = 0;
   cudaStream_t stream = nullptr;       // stream all work is issued on
   cudaStream_t owned_stream = nullptr; // the stream this handle created (destroyed with it)
+  // The kernel tiers of one sub-round of degree group 3 are independent of each other: they are launched on
+  // side streams (fork / join by events) so that their tails and latency-bound phases overlap.
+  cudaStream_t sweep_stream = nullptr; // stream the running sweep launch goes to
+  cudaStream_t side_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  bool overlap_tiers = true;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
@@ -228,8 +235,8 @@ struct GroupSubrounds {
 };
 
 __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, GroupSubrounds gs, uint32_t granule_log2,
-                            uint32_t base_sr, uint32_t large_degree_threshold, uint8_t *keys, uint32_t *vals,
-                            uint32_t *hist, uint32_t *max_deg) {
+                            uint32_t base_sr, uint32_t large_degree_threshold, uint32_t hub_min, uint8_t *keys,
+                            uint32_t *vals, uint32_t *hist, uint32_t *max_deg) {
   uint32_t local_max = 0;
   for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
     const uint32_t d = xadj[u + 1] - xadj[u];
@@ -237,7 +244,7 @@ __global__ void k_list_keys(uint32_t n, const uint32_t *xadj, uint32_t S, GroupS
     if (d == 0 || !(d < large_degree_threshold)) {
       key = kNumTiers * S; // never visited (label_propagation.h:1795, :1914-1915)
     } else {
-      key = tier_of(d) * S + subround_of(u, granule_log2, base_sr, gs.s[degree_group(d)]);
+      key = tier_of(d, hub_min) * S + subround_of(u, granule_log2, base_sr, gs.s[degree_group(d)]);
     }
     keys[u] = static_cast<uint8_t>(key);
     vals[u] = u;
@@ -484,12 +491,12 @@ inline uint32_t grid_for(uint64_t threads_needed, uint32_t block, uint32_t max_b
   return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(b, max_blocks)));
 }
 
-template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS>
+template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS, bool V16 = false>
 void launch_team(kmp_lp_handle *h, const SweepArgs &a, int ctas_per_sm) {
-  const size_t smem = static_cast<size_t>(SLOTS) * TEAMS * 8;
+  const size_t smem = static_cast<size_t>(SLOTS) * TEAMS * (V16 ? 6 : 8);
   const uint32_t want = (a.list_size + TEAMS - 1) / TEAMS;
   const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(want, static_cast<uint32_t>(kSMs * ctas_per_sm)));
-  sweep_team<MODE, EW, P64, T, SLOTS, TEAMS><<<blocks, T * TEAMS, smem, h->stream>>>(a);
+  sweep_team<MODE, EW, P64, T, SLOTS, TEAMS, V16><<<blocks, T * TEAMS, smem, h->sweep_stream>>>(a);
 }
 
 // dynamic shared memory opt-in of the team kernels (per device; called from kmp_lp_create)
@@ -497,7 +504,12 @@ template <int MODE, bool EW, bool P64> void configure_team_kernels() {
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 128, 2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 4 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 512, 8192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
-  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 1024, 16384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+  if constexpr (EW) {
+    cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 1024, 16384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+  } else {
+    cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 1024, 32768, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         32768 * 6);
+  }
 }
 
 template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle *h, int tier, const SweepArgs &a) {
@@ -506,10 +518,10 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
   }
   switch (tier) {
   case 0:
-    sweep_thread<MODE, EW, P64><<<grid_for(a.list_size, 256), 256, 0, h->stream>>>(a);
+    sweep_thread<MODE, EW, P64><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
     break;
   case 1:
-    sweep_warp<MODE, EW, P64><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->stream>>>(a);
+    sweep_warp<MODE, EW, P64><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->sweep_stream>>>(a);
     break;
   case 2: // deg < 256: one warp per vertex, 512 slots
     launch_team<MODE, EW, P64, 32, 512, 8>(h, a, 7);
@@ -520,8 +532,12 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
   case 4: // deg < 4096: 512 threads per vertex, 8192 slots
     launch_team<MODE, EW, P64, 512, 8192, 1>(h, a, 3);
     break;
-  case 5: // deg < 8192: 1024 threads per vertex, 16384 slots
-    launch_team<MODE, EW, P64, 1024, 16384, 1>(h, a, 1);
+  case 5: // 1024 threads per vertex; deg < 8192: 16384 slots, or (unit edge weights) deg < 16384: 32768 slots
+    if constexpr (EW) {
+      launch_team<MODE, EW, P64, 1024, 16384, 1>(h, a, 1);
+    } else {
+      launch_team<MODE, EW, P64, 1024, 32768, 1, true>(h, a, 1);
+    }
     break;
   default: {
     HubArgs hb{};
@@ -545,18 +561,18 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
       hb.item_deg = h->t4_item_deg.p + wv.item_lo;
       hb.num_items = wv.item_hi - wv.item_lo;
       hb.queue = h->ctr32.p + 64 + w; // zeroed with the other per-round counters
-      sweep_hub_aggregate<MODE, EW, P64><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->stream>>>(a, hb, h->m);
+      sweep_hub_aggregate<MODE, EW, P64><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->sweep_stream>>>(a, hb, h->m);
       hb.sel_entry = h->t4_sel_entry.p + wv.sel_lo;
       hb.sel_piece = h->t4_sel_piece.p + wv.sel_lo;
       hb.num_sel_items = wv.sel_hi - wv.sel_lo;
       hb.part_best = h->t4_part_best.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
       hb.part_fav = h->t4_part_fav.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
-      sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->stream>>>(a, hb);
+      sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->sweep_stream>>>(a, hb);
       h->kernel_launches += 2;
     }
     hb.part_best = h->t4_part_best.p;
     hb.part_fav = h->t4_part_fav.p;
-    sweep_hub_final<MODE><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->stream>>>(a, hb);
+    sweep_hub_final<MODE><<<grid_for(static_cast<uint64_t>(a.list_size) * 32, 256), 256, 0, h->sweep_stream>>>(a, hb);
     break;
   }
   }
@@ -565,9 +581,12 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
 
 // timing mode: bracket a section of the stream with an event pair tagged with a stats slot
 // (0..4 sweep tiers, 5 commit-rule kernels, 6 apply + activate)
-int timed_begin(kmp_lp_handle *h, int tag) {
+int timed_begin(kmp_lp_handle *h, int tag, cudaStream_t st = nullptr) {
   if (!h->timing) {
     return -1;
+  }
+  if (st == nullptr) {
+    st = h->stream;
   }
   if (h->sweep_events_used == h->sweep_events.size()) {
     cudaEvent_t x, y;
@@ -578,12 +597,12 @@ int timed_begin(kmp_lp_handle *h, int tag) {
   }
   const int idx = static_cast<int>(h->sweep_events_used++);
   h->sweep_event_group[idx] = tag;
-  cudaEventRecord(h->sweep_events[idx].first, h->stream);
+  cudaEventRecord(h->sweep_events[idx].first, st);
   return idx;
 }
-void timed_end(kmp_lp_handle *h, int idx) {
+void timed_end(kmp_lp_handle *h, int idx, cudaStream_t st = nullptr) {
   if (idx >= 0) {
-    cudaEventRecord(h->sweep_events[idx].second, h->stream);
+    cudaEventRecord(h->sweep_events[idx].second, st == nullptr ? h->stream : st);
   }
 }
 
@@ -595,7 +614,10 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int tier, const SweepArgs &
   SweepArgs a = a_in;
   a.counters = h->ctr64.p + tier;
   a.queue = h->queue.p + static_cast<size_t>(tier) * kNumGroups * h->lists_S + h->cur_sg;
-  const int ev = timed_begin(h, tier);
+  if (h->sweep_stream == nullptr) {
+    h->sweep_stream = h->stream;
+  }
+  const int ev = timed_begin(h, tier, h->sweep_stream);
   const bool ew = h->adjwgt != nullptr;
   const int variant = (mode << 2) | (ew ? 2 : 0) | (h->p64 ? 1 : 0);
   cudaError_t e;
@@ -609,7 +631,7 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int tier, const SweepArgs &
   case 6: e = launch_sweep_t<1, true, false>(h, tier, a); break;
   default: e = launch_sweep_t<1, true, true>(h, tier, a); break;
   }
-  timed_end(h, ev);
+  timed_end(h, ev, h->sweep_stream);
   ++h->kernel_launches;
   ++h->sweep_launches;
   ++h->group_launches[tier];
@@ -651,8 +673,9 @@ int ensure_lists(kmp_lp_handle *h) {
     KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
   }
   k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, gs, h->cfg.sync_granule_log2, base_sr,
-                                                        h->cfg.large_degree_threshold, h->sort_keys_in.p,
-                                                        h->sort_vals_in.p, h->ctr32.p, h->ctr32.p + 300);
+                                                        h->cfg.large_degree_threshold,
+                                                        h->adjwgt != nullptr ? kHubMinDegree : kHubMinDegreeUnit,
+                                                        h->sort_keys_in.p, h->sort_vals_in.p, h->ctr32.p, h->ctr32.p + 300);
   KMP_CUDA(cudaGetLastError());
   size_t tmp_bytes = 0;
   KMP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->sort_keys_in.p, h->sort_keys_out.p,
@@ -975,13 +998,42 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   sa.window = make_window(iter, sg);
   h->cur_subround = q.sr;
   h->cur_sg = sg;
+  int live = 0;
   for (int t = q.first_tier; t <= q.last_tier; ++t) {
+    live += q.size[t] != 0;
+  }
+  // several tiers in this sub-round: fork them onto side streams (per-tier timing mode keeps them serial so
+  // that every tier's CUDA-event time is its own)
+  const bool fork = live > 1 && h->overlap_tiers && !h->timing;
+  if (fork) {
+    KMP_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+  }
+  int side = 0;
+  bool used[3] = {false, false, false};
+  for (int t = q.last_tier; t >= q.first_tier; --t) { // largest degrees first: the longest tails start earliest
     if (q.size[t] == 0) {
       continue;
     }
     sa.list = h->order.p + h->list_off[t * S + q.sr] + q.lo[t];
     sa.list_size = q.hi[t] - q.lo[t];
-    KMP_CUDA(launch_sweep(h, rc.mode, t, sa));
+    h->sweep_stream = h->stream;
+    if (fork && side < 3 && t != q.first_tier) {
+      h->sweep_stream = h->side_stream[side];
+      used[side] = true;
+      KMP_CUDA(cudaStreamWaitEvent(h->sweep_stream, h->ev_fork, 0));
+    }
+    const cudaError_t e = launch_sweep(h, rc.mode, t, sa);
+    if (h->sweep_stream != h->stream) {
+      KMP_CUDA(cudaEventRecord(h->ev_join[side], h->sweep_stream));
+      ++side;
+    }
+    h->sweep_stream = h->stream;
+    KMP_CUDA(e);
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (used[i]) {
+      KMP_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[i], 0));
+    }
   }
   return KMP_OK;
 }
@@ -1234,8 +1286,8 @@ int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, 
   const uint32_t n = h->n;
   const bool two_hop = (1.0 - 1.0 * num_clusters / n) <= h->cfg.two_hop_threshold; // lp_clusterer.cc:164-166
   const int iso = h->cfg.isolated_nodes_strategy;
-  const bool do_iso = (iso == KMP_ISOLATED_MATCH || iso == KMP_ISOLATED_CLUSTER ||
-                       ((iso == KMP_ISOLATED_MATCH_DURING_TWO_HOP || iso == KMP_ISOLATED_CLUSTER_DURING_TWO_HOP) && two_hop));
+  // the CLUSTER variants are refused at kmp_lp_create
+  const bool do_iso = iso == KMP_ISOLATED_MATCH || (iso == KMP_ISOLATED_MATCH_DURING_TWO_HOP && two_hop);
   if (do_iso && h->num_isolated > 1) {
     KMP_CUDA(h->pairs_a.ensure(h->num_isolated)); // reuse as u32 storage
     KMP_CUDA(h->pairs_b.ensure(h->num_isolated));
@@ -1522,7 +1574,12 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     }
     if (cfg->two_hop_strategy == KMP_TWO_HOP_MATCH || cfg->two_hop_strategy == KMP_TWO_HOP_CLUSTER) {
       return fail(KMP_ERR_UNSUPPORTED, "global two-hop MATCH / CLUSTER (label_propagation.h:1030-1191) is an id-ordered "
-                                       "chain: use the *_THREADWISE variants or KMP_SCHEDULE_SEQ_STRICT");
+                                       "chain: use MATCH_THREADWISE or KMP_SCHEDULE_SEQ_STRICT");
+    }
+    if (cfg->two_hop_strategy == KMP_TWO_HOP_CLUSTER_THREADWISE || cfg->isolated_nodes_strategy == KMP_ISOLATED_CLUSTER ||
+        cfg->isolated_nodes_strategy == KMP_ISOLATED_CLUSTER_DURING_TWO_HOP) {
+      return fail(KMP_ERR_UNSUPPORTED, "the CLUSTER post passes (next-fit packing in id order, label_propagation.h:884-1016) "
+                                       "are only implemented by KMP_SCHEDULE_SEQ_STRICT; the sync schedule has the MATCH variants");
     }
   }
   if (cfg->relabel_before_second_phase != 0) { // default false (presets.cc:147)
@@ -1561,6 +1618,21 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_CUDA, "failed to create stream/events");
   }
   h->stream = h->owned_stream;
+  h->sweep_stream = h->stream;
+  for (int i = 0; i < 3; ++i) {
+    if (cudaStreamCreateWithFlags(&h->side_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return fail(KMP_ERR_CUDA, "failed to create side streams");
+    }
+  }
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return fail(KMP_ERR_CUDA, "failed to create events");
+  }
+  if (const char *e = std::getenv("KMP_OVERLAP_TIERS")) { // experiments: 0 = launch the tiers of a sub-round serially
+    h->overlap_tiers = std::atoi(e) != 0;
+  }
   configure_team_kernels<0, false, false>();
   configure_team_kernels<0, false, true>();
   configure_team_kernels<0, true, false>();
@@ -1591,6 +1663,11 @@ int kmp_lp_destroy(kmp_lp_handle *h) {
   }
   cudaEventDestroy(h->ev_begin);
   cudaEventDestroy(h->ev_end);
+  cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < 3; ++i) {
+    cudaEventDestroy(h->ev_join[i]);
+    cudaStreamDestroy(h->side_stream[i]);
+  }
   cudaStreamDestroy(h->owned_stream);
   delete h;
   return KMP_OK;
@@ -2022,6 +2099,7 @@ int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream) {
   // 0 is a valid handle (the legacy default stream, which is what torch uses unless told otherwise);
   // (void*)-1 switches back to the handle's own stream
   h->stream = cuda_stream == reinterpret_cast<void *>(-1) ? h->owned_stream : static_cast<cudaStream_t>(cuda_stream);
+  h->sweep_stream = h->stream;
   return KMP_OK;
 }
 

@@ -5,8 +5,9 @@
 //   tier 2 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512-slot shared-memory hash map
 //   tier 3 (deg 256..1023) sweep_team<T=128>  : 128 threads per vertex, 2048 slots
 //   tier 4 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
-//   tier 5 (deg 4096..8191) sweep_team<T=1024>: one 1024-thread CTA per vertex, 16384 slots
-//   tier 6 (deg >= 8192)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
+//   tier 5 (deg 4096..8191, or ..16383 with unit edge weights: 16-bit ratings) sweep_team<T=1024>: one
+//                          1024-thread CTA per vertex, 16384 / 32768 slots
+//   tier 6 (deg >= 8192 / 16384)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
 //                          2048-edge chunks, ratings merged into a global table region per vertex
 //   (tiers 3..6 together are degree group 3 of the schedule)
 //
@@ -425,9 +426,47 @@ __device__ __forceinline__ Cand team_argmax(int id, int tid, Cand c, Cand *s_red
   return warp_argmax<MODE>(kFull, x);
 }
 
-template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS>
+// Ratings of a team table: 32-bit, or -- V16, unit edge weights only, where a rating is at most the degree
+// < 2^16 -- two 16-bit counters per word (a 32768-slot table then fits one SM's shared memory: 192 KiB).
+template <bool V16> struct TeamVals;
+template <> struct TeamVals<false> {
+  using word = int32_t;
+  static constexpr int kBytesPerSlot = 4;
+  static __device__ __forceinline__ void add(word *v, uint32_t slot, int32_t w) { atomicAdd(&v[slot], w); }
+  static __device__ __forceinline__ int32_t get(const word *v, uint32_t slot) { return v[slot]; }
+  static __device__ __forceinline__ void clear(word *v, uint32_t slot) { v[slot] = 0; }
+};
+template <> struct TeamVals<true> {
+  using word = uint32_t;
+  static constexpr int kBytesPerSlot = 2;
+  static __device__ __forceinline__ void add(word *v, uint32_t slot, int32_t w) {
+    atomicAdd(&v[slot >> 1], static_cast<uint32_t>(w) << ((slot & 1u) * 16u)); // halves never carry: rating < 2^16
+  }
+  static __device__ __forceinline__ int32_t get(const word *v, uint32_t slot) {
+    return static_cast<int32_t>((v[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu);
+  }
+  static __device__ __forceinline__ void clear(word *v, uint32_t slot) { reinterpret_cast<uint16_t *>(v)[slot] = 0; }
+};
+
+template <bool V16>
+__device__ __forceinline__ void team_table_add(uint32_t *keys, typename TeamVals<V16>::word *vals, uint32_t mask,
+                                               bool direct, uint32_t key, int32_t w) {
+  uint32_t slot = direct ? key : (lowbias32(key) & mask);
+  while (true) {
+    const uint32_t prev = atomicCAS(&keys[slot], kEmpty, key);
+    if (prev == kEmpty || prev == key) {
+      TeamVals<V16>::add(vals, slot, w);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS, bool V16 = false>
 __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
   static_assert((SLOTS & (SLOTS - 1)) == 0, "table size must be a power of two");
+  static_assert(!(V16 && EW), "16-bit ratings need unit edge weights");
+  using TV = TeamVals<V16>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ Cand s_red_all[TEAMS][T > 32 ? T / 32 : 1];
   __shared__ uint32_t s_next[TEAMS];
@@ -435,11 +474,12 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
   const int tid = threadIdx.x % T;
   const int bar = 1 + team;
   uint32_t *keys = reinterpret_cast<uint32_t *>(smem_raw) + static_cast<size_t>(team) * SLOTS;
-  int32_t *vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * SLOTS * TEAMS) + static_cast<size_t>(team) * SLOTS;
+  typename TV::word *vals = reinterpret_cast<typename TV::word *>(
+      smem_raw + sizeof(uint32_t) * SLOTS * TEAMS + static_cast<size_t>(team) * SLOTS * TV::kBytesPerSlot);
   Cand *s_red = s_red_all[team];
   for (int s = tid; s < SLOTS; s += T) {
     keys[s] = kEmpty;
-    vals[s] = 0;
+    TV::clear(vals, s);
   }
   unsigned long long edges = 0, nodes = 0;
   // work queue: the next list index is claimed one vertex ahead
@@ -513,7 +553,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < B; ++j) {
         if (kb[j] != kEmpty) {
-          table_add(keys, vals, mask, direct, kb[j], wb[j]);
+          team_table_add<V16>(keys, vals, mask, direct, kb[j], wb[j]);
         }
       }
     }
@@ -529,7 +569,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
         for (uint32_t s = tid; s < cap; s += T) {
           const uint32_t k = keys[s];
           if (k != kEmpty) {
-            const int32_t r = vals[s];
+            const int32_t r = TV::get(vals, s);
             Cand x{r, 0, tie_hash(a.base_tie, u, k), k};
             if (cand_better<0>(x, c)) {
               c = x;
@@ -565,7 +605,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
             for (int j = 0; j < 4; ++j) {
               const uint32_t s = s0 + j * T + tid;
               kk[j] = s < cap ? keys[s] : kEmpty;
-              rr[j] = kk[j] != kEmpty ? vals[s] : 0;
+              rr[j] = kk[j] != kEmpty ? TV::get(vals, s) : 0;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
           const uint32_t k = keys[s];
           if (k != kEmpty) {
             Cand ff;
-            const Cand cc = eval_candidate_w<1>(a, u, own, uw, own_w, k, vals[s], a.weight[k], false, ff);
+            const Cand cc = eval_candidate_w<1>(a, u, own, uw, own_w, k, TV::get(vals, s), a.weight[k], false, ff);
             if (cand_better<1>(cc, c)) {
               c = cc;
             }
@@ -602,7 +642,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
     TeamSync<T>::sync(bar); // all scans done before the slots are cleared
     for (uint32_t s = tid; s < cap; s += T) {
       keys[s] = kEmpty;
-      vals[s] = 0;
+      TV::clear(vals, s);
     }
     if (act && tid == 0) {
       edges += deg;
