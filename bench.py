@@ -272,7 +272,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KMP_BENCH_WORKLOAD", "rmat22"))
+    ap.add_argument("--workload", default=os.environ.get("KMP_BENCH_WORKLOAD"),
+                    help="default: rmat22 (BASELINE config 2) on 1 GPU, rmat24 (config 4: R-MAT scale 24, k=64, "
+                         "2/4/8 x B200) on N > 1")
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer arm (e2e = null)")
@@ -280,6 +282,8 @@ def main():
                     help="refinement: one LabelPropagationRefiner.refine call on a hashed k-way partition (N=1 only); "
                          "contraction: contract_clustering of the LP clustering (SURVEY §8f-1, N=1 only)")
     args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "rmat22" if args.gpus <= 1 else "rmat24"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -350,13 +354,10 @@ def main():
     handle.set_timing(False)
     if args.mode == "contraction":
         return contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank)
-    sharded = None
     if world > 1:
-        # strong scaling: ONE graph, vertex frontier sharded over the ranks, proposals all-gathered
-        # over NCCL between sub-rounds (kaminpar_b200/dist.py)
-        from kaminpar_b200.dist import CudaBackend, ShardedLP
-
-        sharded = ShardedLP(CudaBackend(handle, dev), n, ctx.coarsening.clustering.lp.num_iterations, rank, world)
+        # strong scaling: ONE graph, vertex frontier sharded over the ranks; the library all-gathers the proposal
+        # buffers itself (ncclAllGather on the handle's stream, kmp_lp_dist_init) between sweep and commit
+        handle.dist_init(rank, world)
 
     refine_handle = None
     if args.mode == "refinement":
@@ -374,11 +375,7 @@ def main():
         if refine_handle is not None:
             refine_handle.upload_partition(part0)
             return refine_handle.refine(k, mbw, None)[2]
-        if sharded is None:
-            return handle.cluster(mcw, fetch=False)[1]
-        _, moved, st_sh = sharded.compute_clustering(mcw, fetch=False)
-        sharded_moved[:] = moved
-        return st_sh
+        return handle.cluster(mcw, fetch=False)[1]
 
     def barrier():
         if world > 1:
@@ -433,9 +430,8 @@ def main():
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        tot_ms_max, edges_all = float(tmax[0]), float(t[1])
-        # the driver's per-step stats only hold this rank's share of the scan counters
+        # every rank's stats already hold the whole job's scan counters (ncclAllReduce in the library)
+        tot_ms_max, edges_all = float(tmax[0]), float(edges)
     else:
         tot_ms_max, edges_all = tot_ms, float(edges)
     value = edges_all / (tot_ms_max * 1e-3)
@@ -447,9 +443,8 @@ def main():
 
     e2e_handle = None
     if world > 1:
-        from kaminpar_b200.dist import CudaBackend, ShardedLP
-
         e2e_handle = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
+        e2e_handle.dist_init(rank, world)
 
     refiner = p_graph_host = None
     if args.mode == "refinement":
@@ -468,8 +463,7 @@ def main():
             clusterer.compute_clustering(g_host, clustering=out_np)
             return clusterer.last_stats.edges_scanned
         e2e_handle.set_graph(g_host)  # every rank stages its replica of the graph from pinned host memory
-        drv = ShardedLP(CudaBackend(e2e_handle, dev), n, ctx.coarsening.clustering.lp.num_iterations, rank, world)
-        _, _, st_e = drv.compute_clustering(mcw, fetch=True)
+        _, st_e = e2e_handle.cluster(mcw, out=out_np)
         return st_e.edges_scanned
 
     e2e_edges = 0
@@ -487,8 +481,7 @@ def main():
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_edges = float(tmax[0]), float(t[1])
+        e2e_s = float(tmax[0])
     e2e_value = e2e_edges / e2e_s
     h2d = (n + 1) * 4 + m * 4
     d2h = n * 4
@@ -552,10 +545,9 @@ def main():
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": wl, "n": n, "m_directed": m, "k": k, "mode": args.mode,
                    "max_cluster_weight": mcw,
-                   "iterations": len(sharded_moved) if world > 1 else last.iterations,
-                   "moved": list(sharded_moved) if world > 1 else last.moved_list(),
+                   "iterations": last.iterations, "moved": last.moved_list(),
                    "num_clusters": last.num_clusters, "l2": "inputs_larger_than_l2" if m * 4 > 126e6 else "small_input",
-                   "parallelism": "single" if world == 1 else f"frontier-sharded x{world} (replicated labels, NCCL all-gather of proposals)",
+                   "parallelism": "single" if world == 1 else f"frontier-sharded x{world} (replicated labels; ncclAllGather of the proposal buffers per sub-round inside the library)",
                    "subrounds": ctx.engine.sync_subrounds},
         "clocks": clocks,
         "e2e": None if args.no_e2e else {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d,

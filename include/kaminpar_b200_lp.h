@@ -192,6 +192,19 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out);
  * reference's distributed twin (kaminpar-dist/refinement/lp/lp_refiner.cc:119-222: local
  * perform_iteration per chunk, then label exchange) with NCCL instead of MPI. */
 int kmp_lp_set_shard(kmp_lp_handle *h, uint32_t rank, uint32_t world);
+
+/* NCCL inside the library (what the C++ adapters / the reference's factories use with N GPUs): rank 0 obtains an
+ * id with kmp_lp_dist_unique_id and hands its KMP_DIST_ID_BYTES bytes to the other ranks by any means (MPI, a
+ * file, torch.distributed ...); every rank then calls kmp_lp_dist_init on its handle (= ncclCommInitRank + the
+ * shard of kmp_lp_set_shard). From then on kmp_lp_cluster / kmp_lp_refine run the sharded schedule themselves:
+ * per sub-round the rank sweeps its slice of the work lists, ncclAllGather moves the proposal buffers over
+ * NVLink on the handle's stream, every rank commits. Results equal the single-GPU run bit for bit. libnccl.so.2 is
+ * loaded on demand (KMP_ERR_NCCL if absent). The reference's counterpart is the label exchange of
+ * kaminpar-dist/refinement/lp/lp_refiner.cc:119-222. */
+#define KMP_DIST_ID_BYTES 128
+int kmp_lp_dist_unique_id(void *id_out);
+int kmp_lp_dist_init(kmp_lp_handle *h, const void *id, uint32_t rank, uint32_t world);
+int kmp_lp_dist_shutdown(kmp_lp_handle *h);
 /* Issue all work on the caller's stream (so that it is ordered with the caller's NCCL collectives).
  * 0 = the legacy default stream; (void*)-1 = back to the handle's own stream. */
 int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream);

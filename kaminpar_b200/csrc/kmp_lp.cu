@@ -18,6 +18,8 @@
 #include <vector>
 
 #include <cstdlib>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is dlopen()ed in kmp_lp_dist_init (no link-time dependency)
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -196,6 +198,10 @@ struct kmp_lp_handle {
   uint32_t pull_rounds = 0, push_rounds = 0;
   // frontier sharding (one process per GPU): this rank sweeps slice `rank` of `world` of every list
   uint32_t rank = 0, world = 1;
+  // NCCL communicator of the sharded run (kmp_lp_dist_init): proposals are all-gathered per sub-round on
+  // the handle's stream, inside kmp_lp_cluster / kmp_lp_refine
+  ncclComm_t comm = nullptr;
+  DevBuf<uint32_t> dist_send, dist_recv;
   // stepping API state
   int step_mode = -1;
   uint32_t step_iter = 0; // LP round of the stepping API
@@ -1166,6 +1172,95 @@ void end_iteration(kmp_lp_handle *h, uint32_t moved) {
   h->moved_hist[0] = moved;
 }
 
+// ---- NCCL, loaded on demand ----------------------------------------------------------------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.lib != nullptr) {
+    return KMP_OK;
+  }
+  // an already loaded libnccl.so.2 (e.g. the one torch ships) is reused by the loader; else the system one
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) {
+    lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  }
+  if (lib == nullptr) {
+    return fail(KMP_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror());
+  }
+  NcclApi a;
+  a.lib = lib;
+  a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(lib, "ncclAllGather"));
+  a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.AllReduce || !a.GetErrorString) {
+    return fail(KMP_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+  }
+  g_nccl = a;
+  return KMP_OK;
+}
+
+#define KMP_NCCL(expr)                                                                                     \
+  do {                                                                                                     \
+    ncclResult_t _r = (expr);                                                                              \
+    if (_r != ncclSuccess) {                                                                               \
+      return fail(KMP_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(_r));                    \
+    }                                                                                                      \
+  } while (0)
+
+// Sweep this rank's share of sub-round sg and pack its proposals into d_send (4 + 2 * cap words:
+// [count, -, -, -, u[cap], t[cap]]).
+int dist_sweep_pack(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q, uint32_t *d_send) {
+  h->stepping = true;
+  const int r = sweep_subround(h, rc, iter, sg, q);
+  h->stepping = false;
+  if (r != KMP_OK) {
+    return r;
+  }
+  const uint32_t cap = subround_cap(h, q);
+  k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p,
+                                                                      h->ctr32.p + (h->mover_parity ? 3 : 0), cap, d_send);
+  ++h->kernel_launches;
+  KMP_CUDA(cudaGetLastError());
+  return KMP_OK;
+}
+
+// Commit sub-round sg from the all-gathered proposal buffers (world * (4 + 2 * cap) words): every rank runs
+// the same order-independent commit on the same proposals, so the replicas stay bit-identical.
+int dist_unpack_commit(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q,
+                       const uint32_t *d_gathered) {
+  const uint32_t cap = subround_cap(h, q);
+  const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(d_gathered, h->world, cap, h->mv_u.p, h->mv_t.p,
+                                                                        h->ctr32.p + (h->mover_parity ? 3 : 0));
+  const uint32_t agrid = grid_for(q.total, 256, kSMs * 8);
+  if (rc.mode == 0) {
+    k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt,
+                                                          base_commit, h->incoming.p, h->hist.p, rc.num_labels);
+  } else {
+    const size_t smem_h = rc.num_labels * kLadderLevels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * kLadderLevels * 4 : 0;
+    k_accumulate_movers<1><<<agrid, 256, smem_h, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt,
+                                                               base_commit, h->incoming.p, h->hist.p, rc.num_labels);
+  }
+  h->kernel_launches += 2;
+  KMP_CUDA(cudaGetLastError());
+  h->step_accumulated = true;
+  const int r2 = commit_subround(h, rc, iter, sg, q);
+  h->step_accumulated = false;
+  return r2;
+}
+
 // One LP round over all (group, sub-round) lists. Returns via *moved the accepted moves.
 int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *moved, uint32_t *proposals) {
   const uint32_t S = h->lists_S;
@@ -1173,12 +1268,34 @@ int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *m
   if (rc0 != KMP_OK) {
     return rc0;
   }
+  if (h->world > 1) { // exchange buffers for the largest sub-round, allocated once
+    size_t max_words = 4;
+    for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
+      max_words = std::max<size_t>(max_words, 4 + 2 * static_cast<size_t>(subround_cap(h, subround_of_sg(h, sg))));
+    }
+    KMP_CUDA(h->dist_send.ensure(max_words));
+    KMP_CUDA(h->dist_recv.ensure(std::max<size_t>(max_words * h->world, h->n)));
+  }
   for (uint32_t sg = 0; sg < kNumGroups * S; ++sg) {
     const SubRound q = subround_of_sg(h, sg);
     if (q.total == 0) {
       continue;
     }
-    int rc2 = sweep_subround(h, rc, iter, sg, q);
+    int rc2;
+    if (h->world > 1) { // sharded: sweep the own slice, all-gather the proposals (NVLink), replicated commit
+      const size_t words = 4 + 2 * static_cast<size_t>(subround_cap(h, q));
+      rc2 = dist_sweep_pack(h, rc, iter, sg, q, h->dist_send.p);
+      if (rc2 != KMP_OK) {
+        return rc2;
+      }
+      KMP_NCCL(g_nccl.AllGather(h->dist_send.p, h->dist_recv.p, words, ncclUint32, h->comm, h->stream));
+      rc2 = dist_unpack_commit(h, rc, iter, sg, q, h->dist_recv.p);
+      if (rc2 != KMP_OK) {
+        return rc2;
+      }
+      continue;
+    }
+    rc2 = sweep_subround(h, rc, iter, sg, q);
     if (rc2 != KMP_OK) {
       return rc2;
     }
@@ -1239,6 +1356,9 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
 }
 
 int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
+  if (h->world > 1 && h->comm != nullptr && stats != nullptr) { // every rank reports the whole job's scan counters
+    KMP_NCCL(g_nccl.AllReduce(h->ctr64.p, h->ctr64.p, 16, ncclUint64, ncclSum, h->comm, h->stream));
+  }
   KMP_CUDA(cudaEventRecord(h->ev_end, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   if (stats != nullptr) {
@@ -1651,6 +1771,10 @@ int kmp_lp_destroy(kmp_lp_handle *h) {
   }
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->comm != nullptr) {
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
   kmp_lp_free_scratch(h);
   h->own_xadj.release();
   h->own_adjncy.release();
@@ -1767,6 +1891,10 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   if (h->cfg.schedule == KMP_SCHEDULE_SEQ_STRICT) {
     return strict_cluster(h, max_cluster_weight, desired_num_clusters, communities, clustering_out, stats);
   }
+  if (h->world > 1 && h->comm == nullptr) {
+    return fail(KMP_ERR_INVALID, "sharded handle without a communicator: call kmp_lp_dist_init (or drive the "
+                                 "stepping API yourself)");
+  }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
   if (rc != KMP_OK) {
@@ -1826,6 +1954,12 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
     if (stats != nullptr) {
       stats->num_clusters = num_clusters;
     }
+    if (h->world > 1) { // favored[u] is only written by the rank that swept u: MAX over (favored ^ u), 0 elsewhere
+      KMP_CUDA(h->dist_recv.ensure(n));
+      k_xor_iota<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->favored.p, h->dist_recv.p);
+      KMP_NCCL(g_nccl.AllReduce(h->dist_recv.p, h->dist_recv.p, n, ncclUint32, ncclMax, h->comm, h->stream));
+      k_xor_iota<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->dist_recv.p, h->favored.p);
+    }
     rc = cluster_post_passes(h, max_cluster_weight, num_clusters, stats); // lp_clusterer.cc:107-108
     if (rc != KMP_OK) {
       return rc;
@@ -1873,6 +2007,10 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   }
   if (h->cfg.schedule == KMP_SCHEDULE_SEQ_STRICT) {
     return strict_refine(h, k, max_block_weights, min_block_weights, communities, partition_inout, block_weights_out, stats);
+  }
+  if (h->world > 1 && h->comm == nullptr) {
+    return fail(KMP_ERR_INVALID, "sharded handle without a communicator: call kmp_lp_dist_init (or drive the "
+                                 "stepping API yourself)");
   }
   const uint32_t n = h->n;
   rc = ensure_lists(h);
@@ -2091,6 +2229,62 @@ int kmp_lp_set_shard(kmp_lp_handle *h, uint32_t rank, uint32_t world) {
   return KMP_OK;
 }
 
+// ---- NCCL inside the library: one process per GPU, every rank calls the same entry points ------------------
+int kmp_lp_dist_unique_id(void *id_out) {
+  if (id_out == nullptr) {
+    return fail(KMP_ERR_INVALID, "null argument");
+  }
+  const int rc = load_nccl();
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  ncclUniqueId id;
+  KMP_NCCL(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == KMP_DIST_ID_BYTES, "ncclUniqueId size");
+  std::memcpy(id_out, &id, sizeof(id));
+  return KMP_OK;
+}
+
+int kmp_lp_dist_init(kmp_lp_handle *h, const void *id, uint32_t rank, uint32_t world) {
+  if (h == nullptr || id == nullptr || world == 0 || rank >= world) {
+    return fail(KMP_ERR_INVALID, "bad argument");
+  }
+  if (h->cfg.schedule != KMP_SCHEDULE_SYNC) {
+    return fail(KMP_ERR_UNSUPPORTED, "only the sync schedule shards across GPUs");
+  }
+  const int rc = load_nccl();
+  if (rc != KMP_OK) {
+    return rc;
+  }
+  KMP_CUDA(cudaSetDevice(h->device));
+  if (h->comm != nullptr) {
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  ncclUniqueId nid;
+  std::memcpy(&nid, id, sizeof(nid));
+  if (world > 1) {
+    KMP_NCCL(g_nccl.CommInitRank(&h->comm, static_cast<int>(world), nid, static_cast<int>(rank)));
+  }
+  h->rank = rank;
+  h->world = world;
+  return KMP_OK;
+}
+
+int kmp_lp_dist_shutdown(kmp_lp_handle *h) {
+  if (h == nullptr) {
+    return KMP_OK;
+  }
+  if (h->comm != nullptr) {
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->rank = 0;
+  h->world = 1;
+  return KMP_OK;
+}
+
 int kmp_lp_set_stream(kmp_lp_handle *h, void *cuda_stream) {
   if (h == nullptr) {
     return fail(KMP_ERR_INVALID, "null handle");
@@ -2230,20 +2424,7 @@ int kmp_lp_step_sweep(kmp_lp_handle *h, uint32_t iter, uint32_t sg, void *d_send
     return fail(KMP_ERR_INVALID, "bad argument");
   }
   const RunCtx rc{h->step_mode, h->step_labels, h->step_mcw, h->step_has_min, h->step_has_comm};
-  const SubRound q = subround_of_sg(h, sg);
-  h->stepping = true;
-  int r = sweep_subround(h, rc, iter, sg, q);
-  h->stepping = false;
-  if (r != KMP_OK) {
-    return r;
-  }
-  const uint32_t cap = subround_cap(h, q);
-  k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p,
-                                                                      h->ctr32.p + (h->mover_parity ? 3 : 0), cap,
-                                                                      static_cast<uint32_t *>(d_send));
-  ++h->kernel_launches;
-  KMP_CUDA(cudaGetLastError());
-  return KMP_OK;
+  return dist_sweep_pack(h, rc, iter, sg, subround_of_sg(h, sg), static_cast<uint32_t *>(d_send));
 }
 
 // Commit sub-round sg from the all-gathered proposal buffers (world * (4 + 2 * cap) words).
@@ -2252,26 +2433,7 @@ int kmp_lp_step_commit(kmp_lp_handle *h, uint32_t iter, uint32_t sg, const void 
     return fail(KMP_ERR_INVALID, "bad argument");
   }
   const RunCtx rc{h->step_mode, h->step_labels, h->step_mcw, h->step_has_min, h->step_has_comm};
-  const SubRound q = subround_of_sg(h, sg);
-  const uint32_t cap = subround_cap(h, q);
-  const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
-  k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(static_cast<const uint32_t *>(d_gathered), h->world,
-                                                                        cap, h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0));
-  const uint32_t agrid = grid_for(q.total, 256, kSMs * 8);
-  if (rc.mode == 0) {
-    k_accumulate_movers<0><<<agrid, 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
-                                                          h->incoming.p, h->hist.p, rc.num_labels);
-  } else {
-    const size_t smem_h = rc.num_labels * kLadderLevels <= kSmemPrivLimit ? static_cast<size_t>(rc.num_labels) * kLadderLevels * 4 : 0;
-    k_accumulate_movers<1><<<agrid, 256, smem_h, h->stream>>>(h->mv_u.p, h->mv_t.p, h->ctr32.p + (h->mover_parity ? 3 : 0), h->vwgt, base_commit,
-                                                               h->incoming.p, h->hist.p, rc.num_labels);
-  }
-  h->kernel_launches += 2;
-  KMP_CUDA(cudaGetLastError());
-  h->step_accumulated = true;
-  const int r2 = commit_subround(h, rc, iter, sg, q);
-  h->step_accumulated = false;
-  return r2;
+  return dist_unpack_commit(h, rc, iter, sg, subround_of_sg(h, sg), static_cast<const uint32_t *>(d_gathered));
 }
 
 int kmp_lp_step_end_iteration(kmp_lp_handle *h, uint32_t *moved) {

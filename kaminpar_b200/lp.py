@@ -330,6 +330,23 @@ class LPHandle:
         self._graph_id = None
         self._n = n
 
+    def dist_init(self, rank: int, world: int, group=None):
+        """One process per GPU: create the NCCL communicator inside the library (kmp_lp_dist_init). The id of
+        rank 0 travels through torch.distributed (plumbing only); afterwards cluster() / refine() run the
+        frontier-sharded schedule themselves, collectives included."""
+        uid = (C.c_ubyte * 128)()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+
+            if rank == 0:
+                _check(self._lib.kmp_lp_dist_unique_id(uid))
+            t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, src=0, group=group)
+            for i, b in enumerate(t.cpu().tolist()):
+                uid[i] = b
+        _check(self._lib.kmp_lp_dist_init(self._h, uid, C.c_uint32(rank), C.c_uint32(world)))
+
     def set_timing(self, enabled: bool):
         _check(self._lib.kmp_lp_set_timing(self._h, C.c_int(1 if enabled else 0)))
 

@@ -54,8 +54,10 @@ def run_lp(g, k, steps, warmup, serial):
         # its children, which made the round-1 reference arm single-threaded at N > 1
         avail = host_cores()
         best = None
-        for t in sorted({avail, max(1, avail // 2), max(1, avail // 4), min(avail, 32), min(avail, 16), min(avail, 8)},
-                        reverse=True):
+        # The stand-in's parallel_for (an OpenMP dynamic loop over the reference's own chunk claims) stops scaling
+        # early: R-MAT 22 on a 128-core host measured 1.5-1.8 s/step at 16 threads, 2.2 s at 32, 3.7-4.8 s at 64 and
+        # 150-160 s at 128 (gpurun_out/bench_ref.json, round 2) -- so the sweep stops at 64 threads and reports them all.
+        for t in sorted({min(avail, 64), min(avail, 32), min(avail, 16), min(avail, 8)}, reverse=True):
             B.ref_omp().kmpref_set_num_threads(t)
             fn()
             t0 = time.perf_counter()

@@ -53,6 +53,49 @@ def _run_rank(rank, world, port, out):
             dist.destroy_process_group()
 
 
+def _run_rank_library(rank, world, port, out):
+    """the same job through the library's own NCCL path: kmp_lp_dist_init, then plain cluster() / refine()"""
+    import torch
+    import torch.distributed as dist
+
+    from kaminpar_b200 import lp
+    from kaminpar_b200.graph import rmat
+    from oracle import bindings as B
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g = B.oracle_rearrange(rmat(14, 16, 3))[0]
+        ctx = lp.create_default_context()
+        ctx.engine.seed = 6
+        ctx.engine.device = rank
+        ctx.partition.setup(g, 8, 0.03)
+        mcw = lp.compute_max_cluster_weight(ctx.coarsening, ctx.partition, g.n, g.total_node_weight())
+        h = lp.LPHandle(lp._cluster_config(ctx.coarsening.clustering.lp, ctx.engine))
+        h.dist_init(rank, world)
+        h.set_graph(g)
+        c, st = h.cluster(mcw)
+        c = c.copy()
+        c2, _ = h.cluster(mcw)
+        k = 8
+        part = (np.arange(g.n) % k).astype(np.uint32)
+        h2 = lp.LPHandle(lp._refine_config(ctx.refinement.lp, ctx.engine))
+        h2.dist_init(rank, world)
+        h2.set_graph(g)
+        p, bw, st2 = h2.refine(k, ctx.partition.max_block_weights(), part.copy())
+        # every rank reports the whole job's counters: divide so that _check's sum over ranks is the total
+        np.savez(out + f".{rank}.npz", c=c, c2=c2, p=p, bw=bw, moved=np.array(st.moved_list()),
+                 moved2=np.array(st2.moved_list()), edges=np.array([st.edges_scanned // world]),
+                 edges_rem=np.array([st.edges_scanned % world]))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
 def _check(world, out):
     from kaminpar_b200 import lp
     from kaminpar_b200.graph import rmat
@@ -75,7 +118,7 @@ def _check(world, out):
         assert np.array_equal(d["p"], ep) and np.array_equal(d["bw"], ebw)
         assert list(d["moved"]) == list(st[0].moved[: st[0].iterations])
         assert list(d["moved2"]) == list(st2.moved[: st2.iterations])
-        total_edges += int(d["edges"][0])
+        total_edges += int(d["edges"][0]) + (int(d["edges_rem"][0]) if "edges_rem" in d and rank == 0 else 0)
     assert total_edges == st[0].edges_scanned  # the frontier is partitioned, nothing scanned twice
 
 
@@ -93,6 +136,24 @@ def test_sharded_two_gpus_nccl(tmp_path):
         pytest.skip("needs 2 GPUs")
     out = str(tmp_path / "r")
     mp.spawn(_run_rank, args=(2, 29731, out), nprocs=2, join=True)
+    _check(2, out)
+
+
+def test_library_dist_path_world1(tmp_path):
+    out = str(tmp_path / "r")
+    _run_rank_library(0, 1, 0, out)
+    _check(1, out)
+
+
+def test_library_nccl_two_gpus(tmp_path):
+    """kmp_lp_dist_init + kmp_lp_cluster / kmp_lp_refine: ncclAllGather inside the library, results identical to 1 GPU"""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "r")
+    mp.spawn(_run_rank_library, args=(2, 29741, out), nprocs=2, join=True)
     _check(2, out)
 
 

@@ -310,3 +310,37 @@ def test_t3_quality_next_to_reference(name):
     assert feasible_gpu == feasible_ref or feasible_gpu
     assert cut_gpu < cut_in
     assert cut_gpu <= 1.25 * cut_ref + 16
+
+
+# ------------------------------------------------------------------------------------------------
+# k = 256 (BASELINE config 5), weighted coarse level, device-side metrics
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rmat16_hubs", "rmat15_hubs_w", "grid20", "road60", "rgg_2e15"])
+def test_t1_refinement_k256_and_device_edge_cut(name):
+    """k = 256 blocks (block-weight arrays privatised in shared memory, tables direct-indexed); afterwards
+    kmp_lp_edge_cut on the device == metrics::edge_cut (metrics.cc:36-53) of the same labels."""
+    g = get_graph(name)
+    k = 256
+    if k > g.n // 4:
+        pytest.skip("k too large for this graph")
+    ctx, _ = ctx_for(g, k, seed=12)
+    part = np.random.default_rng(12).integers(0, k, g.n).astype(np.uint32)
+    p_graph = lp.PartitionedGraph(g, k, part)
+    refiner = lp.LabelPropagationRefiner(ctx)
+    refiner.initialize(p_graph)
+    refiner.refine(p_graph, ctx.partition)
+    rp = B.oracle_params(B.default_refine_params(), commit_passes=4)
+    ep, ebw = B.oracle_lp_refine(g, 12, k, ctx.partition.max_block_weights(), part, schedule=B.SYNC, params=rp)
+    assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
+    assert refiner._handle.edge_cut() == B.oracle_edge_cut(g, ep)
+    assert B.oracle_edge_cut(g, ep) < B.oracle_edge_cut(g, part)
+
+
+@pytest.mark.parametrize("name", ["rmat16_hubs", "walshaw_k16", "star_hub"])
+def test_device_edge_cut_of_a_clustering(name):
+    g = get_graph(name)
+    ctx, mcw = ctx_for(g, 8, seed=1)
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    c = clusterer.compute_clustering(g)
+    assert clusterer._handle.edge_cut() == B.oracle_edge_cut(g, c)
