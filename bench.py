@@ -73,9 +73,7 @@ def generate(name, device):
         src, dst = G.rmat_edges_torch(args["scale"], args["edge_factor"], args["seed"], device)
         xadj, adj = G._csr_from_pairs_torch(n, src, dst, device)
     elif kind == "grid":
-        g = G.grid3d(args["nx"])
-        xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)
-        adj = torch.from_numpy(g.adjncy.astype(np.int64)).to(device)
+        xadj, adj = G.grid3d_torch(args["nx"], device)
     elif kind == "rgg":
         g = G.rgg2d(args["n"], args["seed"], device=device)
         xadj = torch.from_numpy(g.xadj.astype(np.int64)).to(device)

@@ -41,6 +41,7 @@ struct CSRGraphView {
   std::span<const NodeID> edges;           // raw_edges(),   m
   std::span<const NodeWeight> node_weights; // raw_node_weights(), n or empty
   std::span<const EdgeWeight> edge_weights; // raw_edge_weights(), m or empty
+  bool sorted = false;                      // CSRGraph::sorted(); read by the seq_strict schedule only
   [[nodiscard]] NodeID n() const { return nodes.empty() ? 0 : static_cast<NodeID>(nodes.size() - 1); }
   [[nodiscard]] EdgeID m() const { return static_cast<EdgeID>(edges.size()); }
   [[nodiscard]] const void *identity() const { return nodes.data(); }
@@ -86,6 +87,7 @@ struct EngineContext { // engine knobs without a reference counterpart
   unsigned sync_subrounds = 8;
   unsigned sync_granule_log2 = 4;
   int device = -1;
+  int schedule = KMP_SCHEDULE_SYNC; // KMP_SCHEDULE_SEQ_STRICT: the reference's one-thread order, bit-identical, small inputs
 };
 
 namespace detail {
@@ -107,6 +109,9 @@ public:
     check(kmp_lp_set_graph(_h, g.n(), g.m(), g.nodes.data(), g.edges.data(),
                            g.node_weights.empty() ? nullptr : g.node_weights.data(),
                            g.edge_weights.empty() ? nullptr : g.edge_weights.data()));
+    if (g.sorted) {
+      check(kmp_lp_set_graph_sorted(_h, 1));
+    }
     _graph_id = g.identity();
     _n = g.n();
     _m = g.m();
@@ -161,6 +166,7 @@ private:
     cfg.sync_subrounds = e.sync_subrounds;
     cfg.sync_granule_log2 = e.sync_granule_log2;
     cfg.device = e.device;
+    cfg.schedule = e.schedule;
     return cfg;
   }
   detail::Handle _handle;
@@ -195,6 +201,7 @@ public:
     return true;
   }
   [[nodiscard]] const kmp_lp_stats &last_stats() const { return _stats; }
+  [[nodiscard]] kmp_lp_handle *handle() const { return _handle.get(); } // e.g. for kmp_lp_dist_init
 
 private:
   static kmp_lp_config make_config(const LabelPropagationRefinementContext &c, const EngineContext &e) {
@@ -209,6 +216,7 @@ private:
     cfg.sync_subrounds = e.sync_subrounds;
     cfg.sync_granule_log2 = e.sync_granule_log2;
     cfg.device = e.device;
+    cfg.schedule = e.schedule;
     return cfg;
   }
   detail::Handle _handle;

@@ -116,6 +116,7 @@ struct kmp_lp_handle {
   // (n <= 2^24 clusterer / k <= 2^24 refiner), else 8 B
   DevBuf<unsigned char> labg;
   bool p64 = false;
+  bool force_p64 = false;
   bool stamps_ok = false;        // 4 * S sub-rounds fit the stamp code (else push activation only)
   bool pull_this = true, pull_next = true; // activation mode of the running / the next LP round
   uint32_t moved_hist[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; // accepted moves of the two previous rounds
@@ -202,6 +203,10 @@ struct kmp_lp_handle {
   // the handle's stream, inside kmp_lp_cluster / kmp_lp_refine
   ncclComm_t comm = nullptr;
   DevBuf<uint32_t> dist_send, dist_recv;
+  // cooperative single-launch commit of the clusterer (lp_commit.cuh commit_cluster_fused)
+  DevBuf<unsigned> grid_bar; // [0] arrivals, [1] generation
+  int fused_blocks = 0;      // co-resident CTAs of the fused kernel (0: not available)
+  bool fused_commit = true;
   // stepping API state
   int step_mode = -1;
   uint32_t step_iter = 0; // LP round of the stepping API
@@ -1044,8 +1049,40 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
   return KMP_OK;
 }
 
+// clusterer, pull activation: the whole commit in one cooperative launch (gathered != nullptr: the sharded run's
+// all-gathered proposal buffers are unpacked and accumulated by the same launch)
+bool can_fuse_commit(const kmp_lp_handle *h, const RunCtx &rc) {
+  return rc.mode == 0 && h->fused_commit && h->fused_blocks > 0 && h->pull_this && h->pull_next;
+}
+int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q,
+                          const uint32_t *gathered) {
+  CommitArgs ca = make_commit_args(h, rc);
+  ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
+  ca.stamp = h->stamps_ok ? make_stamp(iter, sg) : 0;
+  GatheredArgs ga{gathered, h->world, gathered != nullptr ? subround_cap(h, q) : 0u,
+                  h->ctr32.p + (h->mover_parity ? 3 : 0)};
+  GridBarrier bar{h->grid_bar.p, h->grid_bar.p + 1};
+  const uint32_t blocks = std::min<uint32_t>(grid_for(q.total, 256), static_cast<uint32_t>(h->fused_blocks));
+  void *args[] = {&ca, &ga, &bar};
+  const int ev = timed_begin(h, kTagCommit);
+  if (h->p64) {
+    KMP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(commit_cluster_fused<true>), dim3(blocks), dim3(256), args, 0,
+                                         h->stream));
+  } else {
+    KMP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(commit_cluster_fused<false>), dim3(blocks), dim3(256), args,
+                                         0, h->stream));
+  }
+  timed_end(h, ev);
+  ++h->kernel_launches;
+  h->mover_parity ^= 1u;
+  return KMP_OK;
+}
+
 // commit kernels of one sub-round over the proposals in mv_u / mv_t (count in ctr32[0])
 int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q) {
+  if (!h->step_accumulated && can_fuse_commit(h, rc)) {
+    return commit_subround_fused(h, rc, iter, sg, q, nullptr);
+  }
   CommitArgs ca = make_commit_args(h, rc);
   ca.base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   ca.stamp = h->stamps_ok ? make_stamp(iter, sg) : 0;
@@ -1240,6 +1277,9 @@ int dist_sweep_pack(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
 // the same order-independent commit on the same proposals, so the replicas stay bit-identical.
 int dist_unpack_commit(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q,
                        const uint32_t *d_gathered) {
+  if (can_fuse_commit(h, rc)) {
+    return commit_subround_fused(h, rc, iter, sg, q, d_gathered);
+  }
   const uint32_t cap = subround_cap(h, q);
   const uint32_t base_commit = sync_base(h->cfg.seed, h->call_counter, iter * 4096 + sg, SALT_COMMIT);
   k_unpack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(d_gathered, h->world, cap, h->mv_u.p, h->mv_t.p,
@@ -1315,7 +1355,7 @@ int run_iteration(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t *m
 
 // packed gather array: word width by the label range; (re)allocated grow-only
 int prepare_labg(kmp_lp_handle *h, uint32_t num_labels) {
-  h->p64 = num_labels > (1u << 24);
+  h->p64 = num_labels > (1u << 24) || h->force_p64; // KMP_FORCE_P64=1: the 8-byte gather words on small test inputs
   KMP_CUDA(h->labg.ensure(static_cast<size_t>(std::max<uint32_t>(h->n, 1)) * (h->p64 ? 8 : 4)));
   return KMP_OK;
 }
@@ -1749,6 +1789,23 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return fail(KMP_ERR_CUDA, "failed to create events");
+  }
+  {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (coop != 0 &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, commit_cluster_fused<false>, 256, 0) == cudaSuccess &&
+        per_sm > 0 && h->grid_bar.ensure(2) == cudaSuccess && cudaMemset(h->grid_bar.p, 0, 2 * sizeof(unsigned)) == cudaSuccess) {
+      int sms = kSMs;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      h->fused_blocks = sms * std::min(per_sm, 2);
+    }
+    if (const char *e = std::getenv("KMP_FUSED_COMMIT")) { // experiments / tests: 0 = separate commit kernels
+      h->fused_commit = std::atoi(e) != 0;
+    }
+  }
+  if (const char *e = std::getenv("KMP_FORCE_P64")) {
+    h->force_p64 = std::atoi(e) != 0;
   }
   if (const char *e = std::getenv("KMP_OVERLAP_TIERS")) { // experiments: 0 = launch the tiers of a sub-round serially
     h->overlap_tiers = std::atoi(e) != 0;

@@ -99,6 +99,142 @@ __global__ void commit_cluster_decide(const CommitArgs a) {
   }
 }
 
+// ---- clusterer: the whole commit of a sub-round in ONE cooperative launch -------------------------
+// (unpack + accumulate the all-gathered proposals when sharded) -> classify -> decide -> apply, separated by
+// grid-wide barriers instead of kernel boundaries: a sub-round's commit is a few microseconds of work, so
+// three to five launches with their drain / fill gaps cost more than the work itself.
+struct GridBarrier {
+  unsigned *count;        // arrivals of the running barrier (returns to 0)
+  volatile unsigned *gen; // generation, only ever incremented
+};
+__device__ __forceinline__ void grid_sync(const GridBarrier &b) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned g = *b.gen;
+    __threadfence();
+    if (atomicAdd(b.count, 1u) == gridDim.x - 1) {
+      *b.count = 0;
+      __threadfence();
+      atomicAdd(const_cast<unsigned *>(b.gen), 1u);
+    } else {
+      while (*b.gen == g) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct GatheredArgs {              // sharded run: proposal buffers of all ranks, [count, -, -, -, u[cap], t[cap]] each
+  const uint32_t *gathered;        // nullptr: mv_u / mv_t / *mover_count already hold the proposals
+  uint32_t world, cap;
+  uint32_t *mover_count_w;         // writable alias of CommitArgs::mover_count
+};
+
+template <bool P64>
+__global__ void __launch_bounds__(256) commit_cluster_fused(const CommitArgs a, const GatheredArgs ga, const GridBarrier bar) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nth = gridDim.x * blockDim.x;
+  uint32_t cnt;
+  if (ga.gathered != nullptr) {
+    // ---- unpack (rank order) + accumulate incoming[] over ALL proposals
+    const size_t stride = 4 + 2 * static_cast<size_t>(ga.cap);
+    uint32_t total = 0;
+    uint32_t *mv_u = const_cast<uint32_t *>(a.mv_u), *mv_t = const_cast<uint32_t *>(a.mv_t);
+    for (uint32_t r = 0; r < ga.world; ++r) {
+      const uint32_t c = ga.gathered[r * stride];
+      for (uint32_t i = tid; i < c; i += nth) {
+        const uint32_t u = ga.gathered[r * stride + 4 + i];
+        const uint32_t t = ga.gathered[r * stride + 4 + ga.cap + i];
+        mv_u[total + i] = u;
+        mv_t[total + i] = t;
+        atomicAdd(&a.incoming[t], node_weight(a, u));
+      }
+      total += c;
+    }
+    cnt = total;
+    if (tid == 0) {
+      *ga.mover_count_w = total;
+    }
+    grid_sync(bar);
+  } else {
+    cnt = *a.mover_count;
+  }
+  // ---- classify: uncontended targets accept everything; contended ones get a slot and a level histogram
+  for (uint32_t i = tid; i < cnt; i += nth) {
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    if (a.weight[t] + __ldcg(&a.incoming[t]) <= a.max_cluster_weight) {
+      a.acc[i] = 1;
+    } else {
+      const uint32_t prev = atomicCAS(&a.slotmap[t], kEmpty, i);
+      const uint32_t slot = prev == kEmpty ? i : prev;
+      a.cslot[i] = slot;
+      const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+      atomicAdd(&a.chist[static_cast<size_t>(slot) * kLadderLevels + lvl], node_weight(a, u));
+      a.acc[i] = 2;
+    }
+  }
+  grid_sync(bar);
+  // ---- decide (contended proposals): accept iff level >= jmin(target); weights are still the frozen ones
+  for (uint32_t i = tid; i < cnt; i += nth) {
+    if (a.acc[i] != 2) {
+      continue;
+    }
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    const int32_t *h = a.chist + static_cast<size_t>(a.cslot[i]) * kLadderLevels;
+    const int32_t w_t = a.weight[t];
+    int32_t cum = 0;
+    int jm = kLadderLevels;
+#pragma unroll
+    for (int j = kLadderLevels - 1; j >= 0; --j) {
+      cum += __ldcg(&h[j]);
+      if (w_t + cum <= a.max_cluster_weight) {
+        jm = j;
+      }
+    }
+    const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+    a.acc[i] = static_cast<int>(lvl) >= jm ? 1 : 0;
+  }
+  grid_sync(bar);
+  // ---- apply
+  if (tid == 0) {
+    *a.next_mover_count = 0;
+  }
+  uint32_t moved = 0;
+  for (uint32_t i = tid; i < cnt; i += nth) {
+    const uint32_t u = a.mv_u[i];
+    const uint32_t t = a.mv_t[i];
+    a.incoming[t] = 0;
+    if (__ldcg(&a.slotmap[t]) == i) {
+      int32_t *h = a.chist + static_cast<size_t>(i) * kLadderLevels;
+#pragma unroll
+      for (int j = 0; j < kLadderLevels; ++j) {
+        h[j] = 0;
+      }
+      a.slotmap[t] = kEmpty;
+    }
+    if (a.acc[i] == 1) {
+      const uint32_t from = a.label[u];
+      const int32_t w = node_weight(a, u);
+      atomicAdd(&a.weight[t], w);
+      atomicSub(&a.weight[from], w);
+      a.label[u] = t;
+      static_cast<typename LabG<P64>::word *>(a.labg)[u] = LabG<P64>::pack(t, a.stamp);
+      ++moved;
+    } else {
+      a.active[u] = 1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    moved += __shfl_xor_sync(kFull, moved, o);
+  }
+  if ((threadIdx.x & 31) == 0 && moved != 0) {
+    atomicAdd(a.moved_count, moved);
+  }
+}
+
 // ---- refiner ------------------------------------------------------------------------------------
 // suffix sums of the level histograms + reset of the pass state (k threads)
 __global__ void commit_refine_prepare(const CommitArgs a) {

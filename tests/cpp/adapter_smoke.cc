@@ -1,6 +1,7 @@
 // Compiles against the C++ adapters + C ABI; used by tests to check that the header is valid C++20
 // and that the library links. Running it needs a GPU (tests/test_gpu_cpp_adapter.py).
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "kaminpar_b200_adapters.hpp"
@@ -51,6 +52,22 @@ int main() {
     if (!refiner.refine(pg, pc)) return 3;
     if (bw[0] + bw[1] != static_cast<BlockWeight>(g.n()) || bw[0] > 9 || bw[1] > 9) return 4;
     std::printf("adapter ok: clusters via C++ adapters, block weights %d/%d\n", bw[0], bw[1]);
+    // parity hook: ADAPTER_DUMP=<file> gets "n, xadj, adjncy, clustering, partition, block weights" as text so that
+    // tests/test_cpp_adapter.py can compare the adapter's results with the oracle's sync schedule bit for bit
+    if (const char *path = std::getenv("ADAPTER_DUMP")) {
+      if (std::FILE *f = std::fopen(path, "w")) {
+        std::fprintf(f, "%u %u\n", g.n(), g.m());
+        for (EdgeID x : xadj) std::fprintf(f, "%u ", x);
+        std::fprintf(f, "\n");
+        for (NodeID v : adj) std::fprintf(f, "%u ", v);
+        std::fprintf(f, "\n");
+        for (NodeID c : clustering) std::fprintf(f, "%u ", c);
+        std::fprintf(f, "\n");
+        for (BlockID b : part) std::fprintf(f, "%u ", b);
+        std::fprintf(f, "\n%d %d\n", bw[0], bw[1]);
+        std::fclose(f);
+      }
+    }
   } catch (const std::exception &e) {
     std::printf("exception: %s\n", e.what());
     return 1;

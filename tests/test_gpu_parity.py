@@ -175,6 +175,30 @@ def test_t1_activation_mode_does_not_change_results(name, mode, monkeypatch):
     assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
 
 
+@pytest.mark.parametrize("knob", ["KMP_FUSED_COMMIT=0", "KMP_OVERLAP_TIERS=0", "KMP_FORCE_P64=1"])
+@pytest.mark.parametrize("name", ["rmat16_hubs", "rmat15_hubs_w", "road60"])
+def test_t1_launch_structure_knobs_do_not_change_results(name, knob, monkeypatch):
+    """The single cooperative commit launch (vs. classify / decide / apply kernels), the side-stream overlap of
+    the tiers of a sub-round and the width of the packed (label, stamp) gather word (8 bytes once n > 2^24, e.g. the
+    512^3 grid; forced here) are implementation choices only."""
+    monkeypatch.setenv(*knob.split("="))
+    g = get_graph(name)
+    ctx, mcw = ctx_for(g, 8, seed=4)
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    c = clusterer.compute_clustering(g)
+    assert np.array_equal(c, B.oracle_lp_cluster(g, 4, mcw, schedule=B.SYNC))
+    k = 8
+    part = np.random.default_rng(9).integers(0, k, g.n).astype(np.uint32)
+    p_graph = lp.PartitionedGraph(g, k, part)
+    refiner = lp.LabelPropagationRefiner(ctx)
+    refiner.initialize(p_graph)
+    refiner.refine(p_graph, ctx.partition)
+    rp = B.oracle_params(B.default_refine_params(), commit_passes=4)
+    ep, ebw = B.oracle_lp_refine(g, 4, k, ctx.partition.max_block_weights(), part, schedule=B.SYNC, params=rp)
+    assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
+
+
 @pytest.mark.parametrize("name", ["rmat16_hubs", "grid20", "rgg_2e15"])
 def test_t1_long_refinement_switches_to_push_activation(name):
     """Twelve rounds: once few vertices move the engine switches from pull to push activation on its own
