@@ -206,6 +206,7 @@ struct kmp_lp_handle {
   // cooperative single-launch commit of the clusterer (lp_commit.cuh commit_cluster_fused)
   DevBuf<unsigned> grid_bar; // [0] arrivals, [1] generation
   int fused_blocks = 0;      // co-resident CTAs of the fused kernel (0: not available)
+  int fused_blocks_refine = 0;
   bool fused_commit = true;
   // stepping API state
   int step_mode = -1;
@@ -1052,7 +1053,7 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
 // clusterer, pull activation: the whole commit in one cooperative launch (gathered != nullptr: the sharded run's
 // all-gathered proposal buffers are unpacked and accumulated by the same launch)
 bool can_fuse_commit(const kmp_lp_handle *h, const RunCtx &rc) {
-  return rc.mode == 0 && h->fused_commit && h->fused_blocks > 0 && h->pull_this && h->pull_next;
+  return h->fused_commit && (rc.mode == 0 ? h->fused_blocks : h->fused_blocks_refine) > 0 && h->pull_this && h->pull_next;
 }
 int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q,
                           const uint32_t *gathered) {
@@ -1062,9 +1063,29 @@ int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uin
   GatheredArgs ga{gathered, h->world, gathered != nullptr ? subround_cap(h, q) : 0u,
                   h->ctr32.p + (h->mover_parity ? 3 : 0)};
   GridBarrier bar{h->grid_bar.p, h->grid_bar.p + 1};
+  const int ev = timed_begin(h, kTagCommit);
+  if (rc.mode == 1) {
+    uint32_t passes = std::max<uint32_t>(1, h->cfg.sync_commit_passes);
+    const uint32_t k = rc.num_labels;
+    const size_t smem = 4 * std::max<size_t>(k * kLadderLevels <= kSmemPrivLimit ? static_cast<size_t>(k) * kLadderLevels : 0,
+                                             k <= kSmemPrivLimit ? k : 0);
+    const uint32_t blocks = std::min<uint32_t>(grid_for(std::max<uint32_t>(q.total, k), 256),
+                                               static_cast<uint32_t>(h->fused_blocks_refine));
+    void *rargs[] = {&ca, &ga, &bar, &passes};
+    if (h->p64) {
+      KMP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(commit_refine_fused<true>), dim3(blocks), dim3(256), rargs,
+                                           smem, h->stream));
+    } else {
+      KMP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(commit_refine_fused<false>), dim3(blocks), dim3(256), rargs,
+                                           smem, h->stream));
+    }
+    timed_end(h, ev);
+    ++h->kernel_launches;
+    h->mover_parity ^= 1u;
+    return KMP_OK;
+  }
   const uint32_t blocks = std::min<uint32_t>(grid_for(q.total, 256), static_cast<uint32_t>(h->fused_blocks));
   void *args[] = {&ca, &ga, &bar};
-  const int ev = timed_begin(h, kTagCommit);
   if (h->p64) {
     KMP_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(commit_cluster_fused<true>), dim3(blocks), dim3(256), args, 0,
                                          h->stream));
@@ -1799,6 +1820,12 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
       int sms = kSMs;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       h->fused_blocks = sms * std::min(per_sm, 2);
+      int per_sm_r = 0; // refiner kernel with its largest dynamic shared memory (kSmemPrivLimit ints)
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, commit_refine_fused<false>, 256, kSmemPrivLimit * 4) ==
+              cudaSuccess &&
+          per_sm_r > 0) {
+        h->fused_blocks_refine = sms * std::min(per_sm_r, 2);
+      }
     }
     if (const char *e = std::getenv("KMP_FUSED_COMMIT")) { // experiments / tests: 0 = separate commit kernels
       h->fused_commit = std::atoi(e) != 0;
@@ -1897,9 +1924,13 @@ int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *x
   KMP_CUDA(cudaSetDevice(h->device));
   KMP_CUDA(h->own_xadj.ensure(static_cast<size_t>(n) + 1));
   KMP_CUDA(h->own_adjncy.ensure(m));
+  // xadj first, on the handle's stream: the work lists only need the degrees and are built (kernels, a radix
+  // pass, three small host round trips) while the m-sized arrays are still crossing PCIe on a side stream
+  KMP_CUDA(cudaStreamSynchronize(h->stream)); // earlier work may still read the old arrays
   KMP_CUDA(cudaMemcpyAsync(h->own_xadj.p, xadj, (static_cast<size_t>(n) + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+  cudaStream_t big = h->side_stream[0];
   if (m > 0) {
-    KMP_CUDA(cudaMemcpyAsync(h->own_adjncy.p, adjncy, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h->stream));
+    KMP_CUDA(cudaMemcpyAsync(h->own_adjncy.p, adjncy, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, big));
   }
   h->xadj = h->own_xadj.p;
   h->adjncy = h->own_adjncy.p;
@@ -1912,10 +1943,13 @@ int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *x
   }
   if (adjwgt != nullptr) {
     KMP_CUDA(h->own_adjwgt.ensure(m));
-    KMP_CUDA(cudaMemcpyAsync(h->own_adjwgt.p, adjwgt, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, h->stream));
+    KMP_CUDA(cudaMemcpyAsync(h->own_adjwgt.p, adjwgt, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, big));
     h->adjwgt = h->own_adjwgt.p;
   }
-  return set_graph_common(h, n, m);
+  KMP_CUDA(cudaEventRecord(h->ev_join[0], big));
+  const int rc = set_graph_common(h, n, m);
+  KMP_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[0], 0)); // later work on the handle's stream sees the whole graph
+  return rc;
 }
 
 int kmp_lp_set_graph_device(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *d_xadj, const uint32_t *d_adjncy,

@@ -365,6 +365,209 @@ __global__ void commit_refine_reset(const CommitArgs a) {
   }
 }
 
+// ---- refiner: the whole commit of a sub-round in ONE cooperative launch -----------------------------
+// (unpack) -> level histograms -> suffix sums -> passes x (jmin, decide) -> [min-weight ladder] -> apply + reset.
+// The separate kernels above remain for push-activation rounds and as the reference of this fusion; the
+// arithmetic is the same line for line.
+template <bool P64>
+__global__ void __launch_bounds__(256) commit_refine_fused(const CommitArgs a, const GatheredArgs ga, const GridBarrier bar,
+                                                            const uint32_t passes) {
+  extern __shared__ int32_t s_priv[]; // k * 16 ints (level histograms), later k ints (departure / weight deltas)
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nth = gridDim.x * blockDim.x;
+  const bool priv_h = a.k * kLadderLevels <= kSmemPrivLimit;
+  const bool priv_k = a.k <= kSmemPrivLimit;
+  uint32_t cnt;
+  // ---- proposals (unpacked from the all-gathered buffers when sharded), acc = 0, level histograms
+  if (priv_h) {
+    for (uint32_t b = threadIdx.x; b < a.k * kLadderLevels; b += blockDim.x) {
+      s_priv[b] = 0;
+    }
+    __syncthreads();
+  }
+  if (ga.gathered != nullptr) {
+    const size_t stride = 4 + 2 * static_cast<size_t>(ga.cap);
+    uint32_t total = 0;
+    uint32_t *mv_u = const_cast<uint32_t *>(a.mv_u), *mv_t = const_cast<uint32_t *>(a.mv_t);
+    for (uint32_t r = 0; r < ga.world; ++r) {
+      const uint32_t c = ga.gathered[r * stride];
+      for (uint32_t i = tid; i < c; i += nth) {
+        const uint32_t u = ga.gathered[r * stride + 4 + i];
+        const uint32_t t = ga.gathered[r * stride + 4 + ga.cap + i];
+        mv_u[total + i] = u;
+        mv_t[total + i] = t;
+        a.acc[total + i] = 0;
+        const uint32_t slot = t * kLadderLevels + ladder_level(bijective32(u, a.base_commit));
+        atomicAdd(priv_h ? &s_priv[slot] : &a.hist[slot], node_weight(a, u));
+      }
+      total += c;
+    }
+    cnt = total;
+    if (tid == 0) {
+      *ga.mover_count_w = total;
+    }
+  } else {
+    cnt = *a.mover_count;
+    for (uint32_t i = tid; i < cnt; i += nth) {
+      const uint32_t u = a.mv_u[i];
+      a.acc[i] = 0;
+      const uint32_t slot = a.mv_t[i] * kLadderLevels + ladder_level(bijective32(u, a.base_commit));
+      atomicAdd(priv_h ? &s_priv[slot] : &a.hist[slot], node_weight(a, u));
+    }
+  }
+  if (priv_h) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < a.k * kLadderLevels; b += blockDim.x) {
+      if (s_priv[b] != 0) {
+        atomicAdd(&a.hist[b], s_priv[b]);
+      }
+    }
+  }
+  grid_sync(bar);
+  // ---- suffix sums of the level histograms, pass state
+  for (uint32_t b = tid; b < a.k; b += nth) {
+    int32_t cum = 0;
+    for (int j = kLadderLevels - 1; j >= 0; --j) {
+      cum += __ldcg(&a.hist[b * kLadderLevels + j]);
+      a.hist[b * kLadderLevels + j] = cum;
+    }
+    a.out_cur[b] = 0;
+    a.out_delta[b] = 0;
+  }
+  for (uint32_t p = 0; p < passes; ++p) {
+    grid_sync(bar);
+    // ---- jmin per block; folds the previous pass' departures into out_cur
+    for (uint32_t b = tid; b < a.k; b += nth) {
+      const int32_t credit = a.out_cur[b] + __ldcg(&a.out_delta[b]);
+      a.out_cur[b] = credit;
+      a.out_delta[b] = 0;
+      int jm = kLadderLevels;
+      for (int j = 0; j < kLadderLevels; ++j) {
+        if (a.weight[b] + __ldcg(&a.hist[b * kLadderLevels + j]) - credit <= a.max_w[b]) {
+          jm = j;
+          break;
+        }
+      }
+      a.jmin[b] = jm;
+    }
+    if (priv_k) {
+      for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+        s_priv[b] = 0;
+      }
+    }
+    grid_sync(bar);
+    // ---- decide
+    for (uint32_t i = tid; i < cnt; i += nth) {
+      if (a.acc[i] != 0) {
+        continue;
+      }
+      const uint32_t u = a.mv_u[i];
+      const uint32_t t = a.mv_t[i];
+      const uint32_t lvl = ladder_level(bijective32(u, a.base_commit));
+      if (static_cast<int>(lvl) >= __ldcg(&a.jmin[t])) {
+        a.acc[i] = 1;
+        const uint32_t from = a.label[u];
+        if (a.min_w == nullptr || a.min_w[from] <= 0) {
+          atomicAdd(priv_k ? &s_priv[from] : &a.out_delta[from], node_weight(a, u));
+        }
+      }
+    }
+    if (priv_k) {
+      __syncthreads();
+      for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+        if (s_priv[b] != 0) {
+          atomicAdd(&a.out_delta[b], s_priv[b]);
+        }
+      }
+    }
+  }
+  if (a.min_w != nullptr) { // source-side ladder for min block weights
+    grid_sync(bar);
+    for (uint32_t i = tid; i < cnt; i += nth) {
+      if (a.acc[i] == 1) {
+        const uint32_t u = a.mv_u[i];
+        atomicAdd(&a.ohist[a.label[u] * kLadderLevels + ladder_level(bijective32(u, a.base_commit))], node_weight(a, u));
+      }
+    }
+    grid_sync(bar);
+    for (uint32_t b = tid; b < a.k; b += nth) {
+      int32_t cum[kLadderLevels];
+      int32_t c = 0;
+      for (int j = kLadderLevels - 1; j >= 0; --j) {
+        c += __ldcg(&a.ohist[b * kLadderLevels + j]);
+        cum[j] = c;
+        a.ohist[b * kLadderLevels + j] = 0;
+      }
+      int jm = kLadderLevels;
+      for (int j = 0; j < kLadderLevels; ++j) {
+        if (a.weight[b] - cum[j] >= a.min_w[b]) {
+          jm = j;
+          break;
+        }
+      }
+      a.ojmin[b] = jm;
+    }
+    grid_sync(bar);
+    for (uint32_t i = tid; i < cnt; i += nth) {
+      if (a.acc[i] == 1) {
+        const uint32_t u = a.mv_u[i];
+        if (static_cast<int>(ladder_level(bijective32(u, a.base_commit))) < __ldcg(&a.ojmin[a.label[u]])) {
+          a.acc[i] = 0;
+        }
+      }
+    }
+  }
+  grid_sync(bar);
+  // ---- apply + reset of the histograms
+  if (priv_k) {
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      s_priv[b] = 0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *a.next_mover_count = 0;
+  }
+  for (uint32_t b = tid; b < a.k * kLadderLevels; b += nth) {
+    a.hist[b] = 0;
+  }
+  uint32_t moved = 0;
+  for (uint32_t i = tid; i < cnt; i += nth) {
+    const uint32_t u = a.mv_u[i];
+    if (a.acc[i] == 1) {
+      const uint32_t t = a.mv_t[i];
+      const uint32_t from = a.label[u];
+      const int32_t w = node_weight(a, u);
+      if (priv_k) {
+        atomicAdd(&s_priv[t], w);
+        atomicSub(&s_priv[from], w);
+      } else {
+        atomicAdd(&a.weight[t], w);
+        atomicSub(&a.weight[from], w);
+      }
+      a.label[u] = t;
+      static_cast<typename LabG<P64>::word *>(a.labg)[u] = LabG<P64>::pack(t, a.stamp);
+      ++moved;
+    } else {
+      a.active[u] = 1;
+    }
+  }
+  if (priv_k) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < a.k; b += blockDim.x) {
+      if (s_priv[b] != 0) {
+        atomicAdd(&a.weight[b], s_priv[b]);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    moved += __shfl_xor_sync(kFull, moved, o);
+  }
+  if ((threadIdx.x & 31) == 0 && moved != 0) {
+    atomicAdd(a.moved_count, moved);
+  }
+}
+
 // ---- apply (both modes) -----------------------------------------------------------------------
 // One thread per proposal: label, packed (label, stamp) gather word, weights, commit-scratch clean-up
 // (label_propagation.h:826-834). Neighbour activation (label_propagation.h:848-870) is NOT done here: in

@@ -116,9 +116,53 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
           }
           const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
           Cand best = cand_none(), fav = cand_none();
+          bool lazy_done = false;
+          if (MODE == 0 && !skip) {
+            // Clusterer: rank the candidates WITHOUT their cluster weights (one random gather each, DRAM-resident
+            // on large graphs); only the top one is checked. If it is full, fall through to the full evaluation.
+            Cand top = cand_none();
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              if (keys[j] != kEmpty) {
+                bool first = true;
+                int32_t rating = 0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) {
+                  const bool same = keys[q] == keys[j];
+                  rating += same ? ws[q] : 0;
+                  if (q < j && same) {
+                    first = false;
+                  }
+                }
+                if (first && rating > 0) {
+                  const Cand x{rating, 0, tie_hash(a.base_tie, u, keys[j]), keys[j]};
+                  if (cand_better<0>(x, top)) {
+                    top = x;
+                  }
+                  if (store_fav) {
+                    const Cand y{rating, 0, tie_hash(a.base_fav, u, keys[j]), keys[j]};
+                    if (cand_better<0>(y, fav)) {
+                      fav = y;
+                    }
+                  }
+                }
+              }
+            }
+            bool top_ok = true;
+            if (top.gain > 0) {
+              top_ok = (a.weight[top.key] + uw <= a.max_cluster_weight) || (top.key == own);
+              if (a.communities != nullptr) {
+                top_ok = top_ok && (a.communities[top.key] == a.communities[own]);
+              }
+            }
+            if (top_ok) {
+              best = top;
+              lazy_done = true;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            if (!skip && keys[j] != kEmpty) {
+            if (!lazy_done && !skip && keys[j] != kEmpty) {
               bool rep = true;
               int32_t rating = 0;
 #pragma unroll
@@ -136,7 +180,7 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
                   best = c;
                 }
                 if (MODE == 0 && cand_better<0>(f, fav)) {
-                  fav = f;
+                  fav = f; // same value the lazy pass found
                 }
               }
             }
@@ -260,7 +304,7 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
         rating[q] = __popc(peers);
       }
       rep[q] = act[q] && (key[q] != kEmpty) && (lane == __ffs(peers) - 1);
-      kw[q] = rep[q] ? a.weight[key[q]] : 0;
+      kw[q] = (MODE == 1 && rep[q]) ? a.weight[key[q]] : 0; // clusterer: gathered lazily below
     }
 #pragma unroll
     for (int q = 0; q < V; ++q) {
@@ -269,13 +313,41 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
       }
       const bool store_fav = (MODE == 0) && (uw[q] == own_w[q]) && (own_w[q] <= a.max_cluster_weight / 2);
       Cand c = cand_none(), f = cand_none();
-      if (rep[q]) {
-        c = eval_candidate_w<MODE>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], kw[q], store_fav, f);
-      }
-      const Cand best = warp_argmax<MODE>(kFull, c);
-      Cand fav = cand_none();
-      if (MODE == 0 && store_fav) {
-        fav = warp_argmax<0>(kFull, f);
+      Cand best, fav = cand_none();
+      if (MODE == 0) {
+        // rank without the cluster weights; only the top candidate's weight is loaded (one broadcast load).
+        // If that cluster is full, every candidate is evaluated with its weight.
+        if (rep[q] && rating[q] > 0) {
+          c = Cand{rating[q], 0, tie_hash(a.base_tie, u[q], key[q]), key[q]};
+          if (store_fav) {
+            f = Cand{rating[q], 0, tie_hash(a.base_fav, u[q], key[q]), key[q]};
+          }
+        }
+        const Cand top = warp_argmax<0>(kFull, c);
+        if (store_fav) {
+          fav = warp_argmax<0>(kFull, f);
+        }
+        bool top_ok = true;
+        if (top.gain > 0) {
+          top_ok = (a.weight[top.key] + uw[q] <= a.max_cluster_weight) || (top.key == own[q]);
+          if (a.communities != nullptr) {
+            top_ok = top_ok && (a.communities[top.key] == a.communities[own[q]]);
+          }
+        }
+        if (top_ok) {
+          best = top;
+        } else {
+          Cand cf = cand_none(), ff;
+          if (rep[q]) {
+            cf = eval_candidate_w<0>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], a.weight[key[q]], false, ff);
+          }
+          best = warp_argmax<0>(kFull, cf);
+        }
+      } else {
+        if (rep[q]) {
+          c = eval_candidate_w<MODE>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], kw[q], store_fav, f);
+        }
+        best = warp_argmax<MODE>(kFull, c);
       }
       if (lane == 0) {
         edges += deg[q];
