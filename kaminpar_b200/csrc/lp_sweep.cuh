@@ -62,11 +62,14 @@ __device__ __forceinline__ typename LabG<P64>::word load_labg(const SweepArgs &a
 // ================================================================================================
 template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
   constexpr int D = 7;
+  __shared__ uint32_t s_cnt[2][8]; // proposals per warp of the running CTA iteration (parity-double-buffered)
+  __shared__ uint32_t s_base[2];
   unsigned long long edges = 0, nodes = 0;
   const uint32_t stride = gridDim.x * blockDim.x;
-  // the loop bound is rounded up to a full warp so that all lanes reach the ballots
-  const uint32_t bound = (a.list_size + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += stride) {
+  // the loop bound is rounded up to a full CTA so that all threads reach the barriers
+  const uint32_t bound = (a.list_size + 255u) & ~255u;
+  uint32_t it = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += stride, ++it) {
     bool proposes = false;
     uint32_t u = 0, target = 0;
     int32_t uw = 1;
@@ -189,17 +192,30 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
         }
       }
     }
+    // ONE atomic on the proposal counter per CTA iteration (256 vertices): on graphs that live in this tier
+    // (grid, road) nearly every vertex proposes in round 0 and the single address serialises in L2
     const unsigned ballot = __ballot_sync(kFull, proposes);
-    if (ballot != 0) {
-      const int lane = threadIdx.x & 31;
-      uint32_t base = 0;
-      if (lane == 0) {
-        base = atomicAdd(a.mover_count, static_cast<uint32_t>(__popc(ballot)));
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int par = it & 1;
+    if (lane == 0) {
+      s_cnt[par][wib] = static_cast<uint32_t>(__popc(ballot));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int w = 0; w < 8; ++w) {
+        total += s_cnt[par][w];
       }
-      base = __shfl_sync(kFull, base, 0);
-      if (proposes) {
-        emit_proposal<MODE>(a, base + __popc(ballot & ((1u << lane) - 1u)), u, target, uw);
+      s_base[par] = total != 0 ? atomicAdd(a.mover_count, total) : 0u;
+    }
+    __syncthreads();
+    if (proposes) {
+      uint32_t idx = s_base[par] + __popc(ballot & ((1u << lane) - 1u));
+      for (int w = 0; w < wib; ++w) {
+        idx += s_cnt[par][w];
       }
+      emit_proposal<MODE>(a, idx, u, target, uw);
     }
   }
   block_count_flush(a, edges, nodes);
@@ -213,11 +229,26 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
   // label) are issued for the V vertices before any of them is consumed, so a warp keeps V dependent
   // load chains in flight instead of one.
   constexpr int V = 4;
+  // proposals of one CTA iteration (8 warps x V vertices) reserve their slots with ONE atomic on the
+  // proposal counter: on low-degree graphs (RGG, road, grid) nearly every vertex proposes in round 0 and a
+  // per-vertex atomic on that single address serialises in L2
+  __shared__ uint32_t s_cnt[2][8];
+  __shared__ uint32_t s_base[2];
   unsigned long long edges = 0, nodes = 0;
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t i0 = warp * V; i0 < a.list_size; i0 += nwarps * V) {
+  const uint32_t iters = (a.list_size + nwarps * V - 1) / (nwarps * V); // the same for every warp of the grid
+  for (uint32_t it = 0; it < iters; ++it) {
+    const uint32_t i0 = (it * nwarps + warp) * V;
+    bool pr[V];    // lane 0: vertex q proposes a move to pt[q]
+    uint32_t pt[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      pr[q] = false;
+      pt[q] = 0;
+    }
     uint32_t u[V], beg[V], deg[V], own[V];
     int32_t uw[V], own_w[V];
     bool act[V], flag[V], skip[V];
@@ -356,9 +387,38 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
           a.active[u[q]] = 0;
         }
         uint32_t target;
-        if (finish_vertex<MODE>(a, u[q], own[q], store_fav, best, fav, target)) {
-          const uint32_t idx = atomicAdd(a.mover_count, 1u);
-          emit_proposal<MODE>(a, idx, u[q], target, uw[q]);
+        pr[q] = finish_vertex<MODE>(a, u[q], own[q], store_fav, best, fav, target);
+        pt[q] = target;
+      }
+    }
+    uint32_t np = 0;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+      np += pr[q] ? 1u : 0u;
+    }
+    // one slot reservation per CTA iteration (parity-double-buffered, two barriers)
+    const int par = it & 1;
+    if (lane == 0) {
+      s_cnt[par][wib] = np;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int w = 0; w < 8; ++w) {
+        total += s_cnt[par][w];
+      }
+      s_base[par] = total != 0 ? atomicAdd(a.mover_count, total) : 0u;
+    }
+    __syncthreads();
+    if (lane == 0 && np != 0) {
+      uint32_t idx = s_base[par];
+      for (int w = 0; w < wib; ++w) {
+        idx += s_cnt[par][w];
+      }
+#pragma unroll
+      for (int q = 0; q < V; ++q) {
+        if (pr[q]) {
+          emit_proposal<MODE>(a, idx++, u[q], pt[q], uw[q]);
         }
       }
     }
