@@ -1082,7 +1082,20 @@ int sweep_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t s
 // clusterer, pull activation: the whole commit in one cooperative launch (gathered != nullptr: the sharded run's
 // all-gathered proposal buffers are unpacked and accumulated by the same launch)
 bool can_fuse_commit(const kmp_lp_handle *h, const RunCtx &rc) {
-  return h->fused_commit && (rc.mode == 0 ? h->fused_blocks : h->fused_blocks_refine) > 0 && h->pull_this && h->pull_next;
+  return h->fused_commit && (rc.mode == 0 ? h->fused_blocks : h->fused_blocks_refine) > 0;
+}
+// push activation (rounds with few movers): flags for the neighbours of the accepted movers; reads acc[] / mv_u[]
+void launch_push_activation(kmp_lp_handle *h, const CommitArgs &ca, const SubRound &q) {
+  const uint32_t size = q.total;
+  const int ev = timed_begin(h, kTagPush);
+  switch (q.group) {
+  case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
+  }
+  timed_end(h, ev);
+  ++h->kernel_launches;
 }
 int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q,
                           const uint32_t *gathered) {
@@ -1110,6 +1123,9 @@ int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uin
     }
     timed_end(h, ev);
     ++h->kernel_launches;
+    if (!h->pull_this || !h->pull_next) {
+      launch_push_activation(h, ca, q); // acc[] / mv_u[] still hold this sub-round's verdicts
+    }
     h->mover_parity ^= 1u;
     return KMP_OK;
   }
@@ -1124,6 +1140,9 @@ int commit_subround_fused(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uin
   }
   timed_end(h, ev);
   ++h->kernel_launches;
+  if (!h->pull_this || !h->pull_next) {
+    launch_push_activation(h, ca, q);
+  }
   h->mover_parity ^= 1u;
   return KMP_OK;
 }
@@ -1170,17 +1189,8 @@ int commit_subround(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t 
     h->kernel_launches += 1;
   }
   timed_end(h, ev);
-  // push activation (rounds with few movers): BEFORE apply, which rewrites nothing the walk reads
   if (!h->pull_this || !h->pull_next) {
-    ev = timed_begin(h, kTagPush);
-    switch (q.group) {
-    case 0: commit_activate<4><<<grid_for(static_cast<uint64_t>(size) * 4, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-    case 1: commit_activate<8><<<grid_for(static_cast<uint64_t>(size) * 8, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-    case 2: commit_activate<32><<<grid_for(static_cast<uint64_t>(size) * 32, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-    default: commit_activate<256><<<grid_for(static_cast<uint64_t>(size) * 256, 256, kSMs * 6), 256, 0, h->stream>>>(ca); break;
-    }
-    timed_end(h, ev);
-    ++h->kernel_launches;
+    launch_push_activation(h, ca, q);
   }
   ev = timed_begin(h, kTagApply);
   {
