@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -123,6 +124,7 @@ struct kmp_lp_handle {
   uint32_t visited_total = 0;    // vertices on the work lists
   DevBuf<uint32_t> queue;        // work-queue cursors of the team kernels: [tier][sub-round], zeroed per round
   DevBuf<uint32_t> t4_hit;       // hub tier: per list entry "a neighbour moved since the last visit"
+  DevBuf<uint32_t> t4_tmp_deg, t4_tmp_beg, t4_tmp_ids; // list building scratch
   size_t sweep_events_used = 0;
 
   // graph
@@ -679,7 +681,20 @@ cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int tier, const SweepArgs &
   return e;
 }
 
+struct TraceClock { // KMP_TRACE=1: wall-clock stages of set_graph on stderr (diagnostics only)
+  bool on = std::getenv("KMP_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char *what) {
+    if (on) {
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[kmp trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+      t = now;
+    }
+  }
+};
+
 int ensure_lists(kmp_lp_handle *h) {
+  TraceClock tc;
   const uint32_t S = std::max<uint32_t>(1, h->cfg.sync_subrounds);
   if (h->lists_valid && h->lists_S == S && h->lists_G == h->cfg.sync_granule_log2 &&
       h->lists_thr == h->cfg.large_degree_threshold && h->lists_seed == h->cfg.seed) {
@@ -697,6 +712,7 @@ int ensure_lists(kmp_lp_handle *h) {
   KMP_CUDA(h->order.ensure(n));
   KMP_CUDA(h->ctr32.ensure(512));
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
+  tc.lap("lists: buffers");
   const uint32_t base_sr = sync_base(h->cfg.seed, 0, 0, SALT_SUBROUND);
   // Sub-rounds per degree group: S for a group holding >= 1/16 of the visited vertices, S/4 otherwise
   // (a small group has few same-sub-round neighbours; its launches become 4x larger). DESIGN.md §3.
@@ -713,6 +729,7 @@ int ensure_lists(kmp_lp_handle *h) {
     }
     KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
   }
+  tc.lap("lists: group counts (sync)");
   k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, gs, h->cfg.sync_granule_log2, base_sr,
                                                         h->cfg.large_degree_threshold,
                                                         h->adjwgt != nullptr ? kHubMinDegree : kHubMinDegreeUnit,
@@ -729,6 +746,7 @@ int ensure_lists(kmp_lp_handle *h) {
   std::vector<uint32_t> hist(512);
   KMP_CUDA(cudaMemcpyAsync(hist.data(), h->ctr32.p, 512 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
+  tc.lap("lists: keys + sort (sync)");
   h->list_off.assign(nkeys + 1, 0);
   for (uint32_t kx = 0; kx < nkeys; ++kx) {
     h->list_off[kx + 1] = h->list_off[kx] + hist[kx];
@@ -758,7 +776,7 @@ int ensure_lists(kmp_lp_handle *h) {
     h->t4_waves.clear();
     h->t4_max_slots = 0;
     if (t4_cnt > 0) {
-      DevBuf<uint32_t> d_deg, d_beg, d_ids;
+      DevBuf<uint32_t> &d_deg = h->t4_tmp_deg, &d_beg = h->t4_tmp_beg, &d_ids = h->t4_tmp_ids; // grow-only
       KMP_CUDA(d_deg.ensure(t4_cnt));
       KMP_CUDA(d_beg.ensure(t4_cnt));
       KMP_CUDA(d_ids.ensure(t4_cnt));
@@ -772,9 +790,6 @@ int ensure_lists(kmp_lp_handle *h) {
       size_t max_sel = 0;
       KMP_CUDA(cudaMemcpyAsync(deg.data(), d_deg.p, t4_cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
       KMP_CUDA(cudaStreamSynchronize(h->stream));
-      d_deg.release();
-      d_beg.release();
-      d_ids.release();
       // at most kMaxHubWaves work-queue cursors exist per LP round: coarsen the waves if necessary
       // (the degrees must be on the host before this sum -- ADVICE r1)
       uint64_t wave_slots = h->hub_wave_slots;
@@ -859,15 +874,17 @@ int ensure_lists(kmp_lp_handle *h) {
       KMP_CUDA(cudaStreamSynchronize(h->stream));
     }
   }
+  tc.lap("lists: hub metadata");
   h->lists_S = S;
   h->lists_G = h->cfg.sync_granule_log2;
   h->lists_thr = h->cfg.large_degree_threshold;
   h->lists_seed = h->cfg.seed;
   h->lists_valid = true;
   // the sort buffers are only needed here
-  h->sort_keys_in.release();
-  h->sort_keys_out.release();
-  h->sort_vals_in.release();
+  // The sort buffers stay allocated (grow-only, released by kmp_lp_free_scratch): a cudaFree / cudaMalloc pair per
+  // set_graph synchronises the whole device and cost 8-12 ms per call on the bench box -- up to 0.6 s on another --
+  // while the graph upload was in flight (scripts/e2e_probe.py).
+  tc.lap("lists: done");
   return KMP_OK;
 }
 
@@ -1858,12 +1875,14 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
         per_sm > 0 && h->grid_bar.ensure(2) == cudaSuccess && cudaMemset(h->grid_bar.p, 0, 2 * sizeof(unsigned)) == cudaSuccess) {
       int sms = kSMs;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      h->fused_blocks = sms * std::min(per_sm, 2);
+      // all co-resident CTAs: a sub-round of a 10^8-vertex graph commits 10^7 proposals, each a short chain of
+      // dependent random accesses -- the grid is sized by the proposal count up to this limit
+      h->fused_blocks = sms * per_sm;
       int per_sm_r = 0; // refiner kernel with its largest dynamic shared memory (kSmemPrivLimit ints)
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, commit_refine_fused<false>, 256, kSmemPrivLimit * 4) ==
               cudaSuccess &&
           per_sm_r > 0) {
-        h->fused_blocks_refine = sms * std::min(per_sm_r, 2);
+        h->fused_blocks_refine = sms * per_sm_r;
       }
     }
     if (const char *e = std::getenv("KMP_FUSED_COMMIT")) { // experiments / tests: 0 = separate commit kernels
@@ -1967,7 +1986,11 @@ int kmp_lp_set_graph(kmp_lp_handle *h, uint32_t n, uint32_t m, const uint32_t *x
   // pass, three small host round trips) while the m-sized arrays are still crossing PCIe on a side stream
   KMP_CUDA(cudaStreamSynchronize(h->stream)); // earlier work may still read the old arrays
   KMP_CUDA(cudaMemcpyAsync(h->own_xadj.p, xadj, (static_cast<size_t>(n) + 1) * 4, cudaMemcpyHostToDevice, h->stream));
-  cudaStream_t big = h->side_stream[0];
+  static const bool overlap_upload = [] { // experiments: KMP_UPLOAD_OVERLAP=0 copies everything on the handle's stream
+    const char *e = std::getenv("KMP_UPLOAD_OVERLAP");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  cudaStream_t big = overlap_upload ? h->side_stream[0] : h->stream;
   if (m > 0) {
     KMP_CUDA(cudaMemcpyAsync(h->own_adjncy.p, adjncy, static_cast<size_t>(m) * 4, cudaMemcpyHostToDevice, big));
   }
@@ -2308,6 +2331,12 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ctr64.release();
   h->hub_tab.release();
   h->labg.release();
+  h->sort_keys_in.release();
+  h->sort_keys_out.release();
+  h->sort_vals_in.release();
+  h->t4_tmp_deg.release();
+  h->t4_tmp_beg.release();
+  h->t4_tmp_ids.release();
   h->cub_tmp.release();
   h->pairs_a.release();
   h->pairs_b.release();

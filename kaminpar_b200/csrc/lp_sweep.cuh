@@ -702,11 +702,15 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
           const uint32_t k = keys[s];
           if (k != kEmpty) {
             const int32_t r = TV::get(vals, s);
-            Cand x{r, 0, tie_hash(a.base_tie, u, k), k};
-            if (cand_better<0>(x, c)) {
-              c = x;
+            // an entry rated below the thread's running maximum cannot win: its tie hashes are never computed
+            // (most entries of a late-round neighbourhood have rating 1 next to a few heavy clusters)
+            if (r >= c.gain) {
+              Cand x{r, 0, tie_hash(a.base_tie, u, k), k};
+              if (cand_better<0>(x, c)) {
+                c = x;
+              }
             }
-            if (store_fav) {
+            if (store_fav && r >= f.gain) {
               Cand y{r, 0, tie_hash(a.base_fav, u, k), k};
               if (cand_better<0>(y, f)) {
                 f = y;
