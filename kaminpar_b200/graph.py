@@ -126,6 +126,64 @@ def write_metis(g: CSRGraph, path: str) -> None:
 # --------------------------------------------------------------------------------------------
 # Edge list -> symmetric CSR (torch: runs on CPU or CUDA)
 # --------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# ParHIP binary format + partition files (reference: docs/graph_file_format.md,
+# kaminpar-io/parhip_parser.cc:42-93, kaminpar-io/kaminpar_io.cc:58-75)
+# --------------------------------------------------------------------------------------------
+def read_parhip(path: str) -> CSRGraph:
+    """24-byte header (version bit-field, n, m), offsets (file addresses of each adjacency list), adjacency lists,
+    optional node / edge weights. Version bits (0 = present / 64-bit): 1 edge weights, 2 node weights, 4 edge-id
+    width, 8 node-id width, 16 node-weight width, 32 edge-weight width (parhip_parser.cc:80-93)."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    version, n, m = (int(x) for x in raw[:24].view("<u8"))
+    has_ew, has_nw = (version & 1) == 0, (version & 2) == 0
+    eid = np.dtype("<u8") if (version & 4) == 0 else np.dtype("<u4")
+    nid = np.dtype("<u8") if (version & 8) == 0 else np.dtype("<u4")
+    nwt = np.dtype("<i8") if (version & 16) == 0 else np.dtype("<i4")
+    ewt = np.dtype("<i8") if (version & 32) == 0 else np.dtype("<i4")
+    pos = 24
+    offsets = raw[pos:pos + (n + 1) * eid.itemsize].view(eid).astype(np.int64)
+    pos += (n + 1) * eid.itemsize
+    base = 24 + (n + 1) * eid.itemsize  # _nodes_offset_base
+    xadj = (offsets - base) // nid.itemsize  # map_edge_offset (parhip_parser.cc:112-114)
+    adjncy = raw[pos:pos + m * nid.itemsize].view(nid)
+    pos += m * nid.itemsize
+    vwgt = adjwgt = None
+    if has_nw:
+        vwgt = raw[pos:pos + n * nwt.itemsize].view(nwt).astype(np.int32)
+        pos += n * nwt.itemsize
+    if has_ew:
+        adjwgt = raw[pos:pos + m * ewt.itemsize].view(ewt).astype(np.int32)
+    if int(xadj[-1]) != m or (m and int(adjncy.max()) >= n):
+        raise ValueError(f"{path}: inconsistent ParHIP file")
+    return CSRGraph(xadj.astype(np.uint32), adjncy.astype(np.uint32), vwgt, adjwgt)
+
+
+def write_parhip(g: CSRGraph, path: str) -> None:
+    """32-bit ids and weights (the default build's widths, kaminpar.h:32-57)."""
+    has_nw, has_ew = g.vwgt is not None, g.adjwgt is not None
+    version = (0 if has_ew else 1) | (0 if has_nw else 2) | 4 | 8 | 16 | 32
+    base = 24 + (g.n + 1) * 4
+    with open(path, "wb") as f:
+        np.array([version, g.n, g.m], "<u8").tofile(f)
+        (g.xadj.astype(np.int64) * 4 + base).astype("<u4").tofile(f)
+        g.adjncy.astype("<u4").tofile(f)
+        if has_nw:
+            g.vwgt.astype("<i4").tofile(f)
+        if has_ew:
+            g.adjwgt.astype("<i4").tofile(f)
+
+
+def write_partition(path: str, partition) -> None:
+    """One block id per line (kaminpar_io.cc:58-63)."""
+    np.savetxt(path, np.asarray(partition, dtype=np.int64), fmt="%d")
+
+
+def read_partition(path: str) -> np.ndarray:
+    """kaminpar_io.cc:65-75"""
+    return np.loadtxt(path, dtype=np.int64, ndmin=1).astype(np.uint32)
+
+
 def _csr_from_pairs_torch(n: int, src, dst, device):
     """Symmetrise, drop self-loops and duplicates, return (xadj:int64[n+1], adjncy:int64[m])."""
     import torch

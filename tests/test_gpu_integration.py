@@ -59,3 +59,22 @@ def test_compute_partition_through_swapped_factories(name, k, cut_bound):
     ref_cut, _ = partition(_load(LIB_FULL), g, k)
     print(f"{name} k={k}: cut with the B200 LP {cut}, pure reference {ref_cut}")
     assert cut <= 1.25 * ref_cut + 16
+
+
+def test_python_facade_over_the_integrated_build():
+    """kaminpar_b200.facade.KaMinPar mirrors the reference's facade (kaminpar.h:857-997) on top of the integrated
+    build: copy_graph / set_k / set_uniform_max_block_weights / compute_partition / reseed."""
+    if not os.path.exists(LIB_B200):
+        pytest.skip("integrated build not available")
+    from kaminpar_b200.facade import KaMinPar
+
+    g = H.load_graph("walshaw_data")
+    KaMinPar.reseed(0)
+    shm = KaMinPar(num_threads=1)
+    shm.copy_graph(g.xadj, g.adjncy)
+    shm.set_k(16)
+    shm.set_uniform_max_block_weights(0.03)
+    cut, part = shm.compute_partition()
+    assert (part < 16).all() and cut == B.oracle_edge_cut(g, part) and cut <= 2000
+    cut2, part2 = shm.compute_partition()
+    assert cut2 == cut and np.array_equal(part, part2)
