@@ -23,6 +23,8 @@
 // ceil(2b/8) radix passes of 24 B each.
 #pragma once
 
+#include <mutex>
+
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_reduce.cuh>
 #include <cub/device/device_run_length_encode.cuh>
@@ -31,23 +33,55 @@
 // loop allocates and frees coarse graphs of hundreds of MB per level, and cudaMalloc / cudaFree of that
 // size cost milliseconds and serialise the device. The pool keeps freed blocks (release threshold set
 // in contract_impl), so after the first level an allocation is a pointer bump.
+// A PRIVATE pool per device (never the device's default pool, which the host application or torch's
+// cudaMallocAsync backend may share -- ADVICE r1): freed blocks stay in it until kmp_lp_free_scratch trims it.
+inline cudaMemPool_t kmp_private_pool(int device) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) {
+    return nullptr;
+  }
+  if (pools[device] == nullptr) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      pools[device] = pool;
+    }
+  }
+  return pools[device];
+}
+
 template <typename T> struct PoolBuf {
   T *p = nullptr;
   size_t cap = 0;
-  cudaError_t alloc(size_t n, cudaStream_t st) {
+  cudaStream_t stream = nullptr; // the stream the block was allocated on: it is freed there, too
+  cudaError_t alloc(size_t n, cudaStream_t st, int device) {
     release();
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&p), std::max<size_t>(n, 1) * sizeof(T), st);
+    cudaMemPool_t pool = kmp_private_pool(device);
+    if (pool == nullptr) {
+      return cudaErrorMemoryAllocation;
+    }
+    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&p), std::max<size_t>(n, 1) * sizeof(T), pool, st);
     if (e == cudaSuccess) {
       cap = std::max<size_t>(n, 1);
+      stream = st;
     } else {
       p = nullptr;
     }
     return e;
   }
-  // all work on the buffer has completed when this is called (contract_impl synchronises its stream)
+  // stream-ordered: a later user of the arrays (e.g. the next level's LP handle) must have synchronised with
+  // `stream` before the coarse graph is destroyed (kmp_coarse_destroy documents it)
   void release() {
     if (p != nullptr) {
-      cudaFreeAsync(p, nullptr);
+      cudaFreeAsync(p, stream);
     }
     p = nullptr;
     cap = 0;
@@ -238,15 +272,9 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   uint32_t launches = 0;
   cg->device = h->device;
   cg->fine_n = n;
-  {
-    cudaMemPool_t pool = nullptr;
-    KMP_CUDA(cudaDeviceGetDefaultMemPool(&pool, h->device));
-    unsigned long long keep = ~0ull; // freed blocks stay in the pool (kmp_lp_free_scratch trims it)
-    KMP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
-  KMP_CUDA(cg->mapping.alloc(n, st));
+  KMP_CUDA(cg->mapping.alloc(n, st, h->device));
   if (n == 0) {
-    KMP_CUDA(cg->xadj.alloc(1, st));
+    KMP_CUDA(cg->xadj.alloc(1, st, h->device));
     KMP_CUDA(cudaMemsetAsync(cg->xadj.p, 0, sizeof(uint32_t), st));
     KMP_CUDA(cudaStreamSynchronize(st));
     return KMP_OK;
@@ -264,7 +292,12 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
     }
     cl = h->label.p;
   }
-  cudaEvent_t ev0 = h->ev_begin, ev1 = h->ev_end; // not inside an LP call: the handle's event pair is free
+  // a dedicated event pair (the handle's own pair may bracket an open stepping call -- ADVICE r1)
+  if (h->ev_ct0 == nullptr) {
+    KMP_CUDA(cudaEventCreate(&h->ev_ct0));
+    KMP_CUDA(cudaEventCreate(&h->ev_ct1));
+  }
+  cudaEvent_t ev0 = h->ev_ct0, ev1 = h->ev_ct1;
   KMP_CUDA(cudaEventRecord(ev0, st));
   // ---- 1. mapping ------------------------------------------------------------------------------
   KMP_CUDA(flags.ensure(static_cast<size_t>(n) + 1)); // flags[n]: out-of-range marker
@@ -284,7 +317,7 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   }
   const uint32_t c_n = host2[0];
   cg->c_n = c_n;
-  KMP_CUDA(cg->vwgt.alloc(c_n, st));
+  KMP_CUDA(cg->vwgt.alloc(c_n, st, h->device));
   KMP_CUDA(cudaMemsetAsync(cg->vwgt.p, 0, static_cast<size_t>(c_n) * 4, st));
   k_map_and_weigh<<<grid_for(n, 256), 256, 0, st>>>(n, cl, rank.p, h->vwgt, cg->mapping.p, cg->vwgt.p);
   launches += 4;
@@ -321,7 +354,7 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
   }
   // ---- 3. sort + reduce by key -----------------------------------------------------------------
   uint32_t c_m = 0;
-  KMP_CUDA(cg->xadj.alloc(static_cast<size_t>(c_n) + 1, st));
+  KMP_CUDA(cg->xadj.alloc(static_cast<size_t>(c_n) + 1, st, h->device));
   if (cut > 0) {
     const int items = static_cast<int>(cut);
     KMP_CUDA(keys_b.ensure(cut));
@@ -357,8 +390,8 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
     KMP_CUDA(cudaMemcpyAsync(&c_m, num_runs, 4, cudaMemcpyDeviceToHost, st));
     KMP_CUDA(cudaStreamSynchronize(st));
     // ---- 4. CSR assembly -------------------------------------------------------------------------
-    KMP_CUDA(cg->adjncy.alloc(c_m, st));
-    KMP_CUDA(cg->adjwgt.alloc(c_m, st));
+    KMP_CUDA(cg->adjncy.alloc(c_m, st, h->device));
+    KMP_CUDA(cg->adjwgt.alloc(c_m, st, h->device));
     KMP_CUDA(cudaMemcpyAsync(cg->adjwgt.p, uw, static_cast<size_t>(c_m) * 4, cudaMemcpyDeviceToDevice, st));
     k_coarse_offsets<<<grid_for(static_cast<uint64_t>(c_n) + 1, 256), 256, 0, st>>>(c_n, c_m, uk, shift, cg->xadj.p);
     k_coarse_targets<<<grid_for(c_m, 256), 256, 0, st>>>(c_m, uk, shift, cg->adjncy.p);
@@ -366,8 +399,8 @@ int contract_impl(kmp_lp_handle *h, const uint32_t *clustering, kmp_coarse_graph
     KMP_CUDA(cudaGetLastError());
   } else {
     KMP_CUDA(cudaMemsetAsync(cg->xadj.p, 0, (static_cast<size_t>(c_n) + 1) * 4, st));
-    KMP_CUDA(cg->adjncy.alloc(1, st));
-    KMP_CUDA(cg->adjwgt.alloc(1, st));
+    KMP_CUDA(cg->adjncy.alloc(1, st, h->device));
+    KMP_CUDA(cg->adjwgt.alloc(1, st, h->device));
   }
   cg->c_m = c_m;
   KMP_CUDA(cudaEventRecord(ev1, st));

@@ -97,6 +97,8 @@ template <typename T> struct DevBuf {
 
 } // namespace
 
+cudaMemPool_t kmp_private_pool(int device); // kmp_contract.cuh
+
 struct kmp_lp_handle {
   kmp_lp_config cfg{};
   int device = 0;
@@ -109,6 +111,7 @@ struct kmp_lp_handle {
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   bool overlap_tiers = true;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_ct0 = nullptr, ev_ct1 = nullptr; // contraction timing (kmp_contract.cuh), created on first use
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
   std::vector<int> sweep_event_group;
@@ -1929,6 +1932,10 @@ int kmp_lp_destroy(kmp_lp_handle *h) {
   }
   cudaEventDestroy(h->ev_begin);
   cudaEventDestroy(h->ev_end);
+  if (h->ev_ct0 != nullptr) {
+    cudaEventDestroy(h->ev_ct0);
+    cudaEventDestroy(h->ev_ct1);
+  }
   cudaEventDestroy(h->ev_fork);
   for (int i = 0; i < 3; ++i) {
     cudaEventDestroy(h->ev_join[i]);
@@ -1948,6 +1955,9 @@ int kmp_lp_set_timing(kmp_lp_handle *h, int enabled) {
 }
 
 static int set_graph_common(kmp_lp_handle *h, uint32_t n, uint32_t m) {
+  if (n > 0x7FFFFFFFu || m > 0x7FFFFFFFu) { // CUB scans / sorts take int counts; 32-bit EdgeID build of the reference
+    return fail(KMP_ERR_UNSUPPORTED, "n and m must be below 2^31");
+  }
   h->n = n;
   h->m = m;
   h->have_graph = true;
@@ -2347,8 +2357,8 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ct_cl.release();
   h->ct_counter.release();
   {
-    cudaMemPool_t pool = nullptr; // blocks cached for coarse graphs (kmp_contract.cuh)
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+    cudaMemPool_t pool = kmp_private_pool(h->device); // blocks cached for coarse graphs (kmp_contract.cuh)
+    if (pool != nullptr) {
       cudaMemPoolTrimTo(pool, 0);
     }
   }
