@@ -117,6 +117,9 @@ public:
     _m = g.m();
   }
   [[nodiscard]] kmp_lp_handle *get() const { return _h; }
+  // The borrowed graph is recognised by (address, n, m): call this when its arrays were rewritten in place (or
+  // freed and reallocated at the same address) so that the next call uploads it again.
+  void invalidate_graph() { _graph_id = nullptr; }
 
 private:
   kmp_lp_handle *_h = nullptr;
@@ -148,6 +151,7 @@ public:
   }
   [[nodiscard]] const kmp_lp_stats &last_stats() const { return _stats; }
   [[nodiscard]] kmp_lp_handle *handle() const { return _handle.get(); } // graph holder for contract_clustering
+  void invalidate_graph() { _handle.invalidate_graph(); }                // the borrowed graph changed in place
 
 private:
   static kmp_lp_config make_config(const LabelPropagationCoarseningContext &c, const EngineContext &e) {
@@ -202,6 +206,7 @@ public:
   }
   [[nodiscard]] const kmp_lp_stats &last_stats() const { return _stats; }
   [[nodiscard]] kmp_lp_handle *handle() const { return _handle.get(); } // e.g. for kmp_lp_dist_init
+  void invalidate_graph() { _handle.invalidate_graph(); }
 
 private:
   static kmp_lp_config make_config(const LabelPropagationRefinementContext &c, const EngineContext &e) {

@@ -63,13 +63,13 @@ typedef struct {
                                       insertion order, lp_clusterer.cc:252-278) has no order-free restatement:
                                       KMP_ERR_UNSUPPORTED under schedule KMP_SCHEDULE_SYNC, implemented by
                                       KMP_SCHEDULE_SEQ_STRICT */
-  int32_t two_hop_strategy;        /* clusterer only. SYNC: DISABLE and MATCH_THREADWISE (default); the global
-                                      MATCH / CLUSTER variants (label_propagation.h:1030-1191, an id-ordered chain
-                                      of CAS hand-offs) and CLUSTER_THREADWISE (next-fit packing in id order) are
+  int32_t two_hop_strategy;        /* clusterer only. SYNC: DISABLE, MATCH_THREADWISE (default) and CLUSTER_THREADWISE
+                                      (the one-thread outcome: pairs / next-fit packing of the singletons that favor the
+                                      same cluster, in id order, label_propagation.h:977-1002); the global MATCH /
+                                      CLUSTER variants (:1030-1191, an id-ordered chain of CAS hand-offs) are
                                       KMP_ERR_UNSUPPORTED under SYNC and implemented by SEQ_STRICT */
   double two_hop_threshold;        /* 0.5 */
-  int32_t isolated_nodes_strategy; /* clusterer only. SYNC: KEEP, MATCH, MATCH_DURING_TWO_HOP (default); the
-                                      CLUSTER variants are KMP_ERR_UNSUPPORTED under SYNC, implemented by SEQ_STRICT */
+  int32_t isolated_nodes_strategy; /* clusterer only; all five values (CLUSTER = next-fit packing in id order) */
   int32_t relabel_before_second_phase; /* must be 0 (the default, presets.cc:147); the cluster-id compaction of
                                       label_propagation.h:272-319 is not implemented: non-zero = KMP_ERR_UNSUPPORTED */
   /* engine */

@@ -391,20 +391,21 @@ __device__ __forceinline__ uint32_t warp_append_slot(uint32_t *count, bool pred)
 
 // ---- post passes of the clusterer (sync definitions) ---------------------------------
 // isolated nodes: the i-th and (i+1)-th isolated vertex (i even, id order) are matched if they fit
-__global__ void k_collect_isolated(uint32_t n, const uint32_t *xadj, uint32_t *list, uint32_t *count) {
+// isolated vertices as (0, u) pairs: one group of the pair-based post passes below
+__global__ void k_collect_isolated(uint32_t n, const uint32_t *xadj, unsigned long long *pairs, uint32_t *count) {
   const uint32_t bound = (n + 31u) & ~31u; // whole warps reach the ballot
   for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < bound; u += gridDim.x * blockDim.x) {
     const bool iso = u < n && xadj[u + 1] == xadj[u];
     const uint32_t slot = warp_append_slot(count, iso);
     if (iso) {
-      list[slot] = u;
+      pairs[slot] = u;
     }
   }
 }
-__global__ void k_match_isolated(uint32_t cnt, const uint32_t *sorted_iso, uint32_t *label, int32_t *weight,
+__global__ void k_match_isolated(uint32_t cnt, const unsigned long long *sorted_iso, uint32_t *label, int32_t *weight,
                                  int32_t max_w) {
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; 2 * p + 1 < cnt; p += gridDim.x * blockDim.x) {
-    const uint32_t a = sorted_iso[2 * p], b = sorted_iso[2 * p + 1];
+    const uint32_t a = static_cast<uint32_t>(sorted_iso[2 * p]), b = static_cast<uint32_t>(sorted_iso[2 * p + 1]);
     const uint32_t ca = label[a], cb = label[b];
     if (ca != cb && weight[ca] + weight[cb] <= max_w) {
       weight[ca] += weight[cb];
@@ -439,6 +440,71 @@ __global__ void k_two_hop_heads(uint32_t cnt, const unsigned long long *sorted, 
     head[p] = is_head ? p : 0u;
   }
 }
+// CLUSTER post passes (next fit in id order = the reference at one thread: label_propagation.h:884-917 for isolated
+// vertices, :977-1002 with match = false for two-hop): within a group of equal key (sorted by vertex id) a vertex
+// joins the waiting representative while it has room, else becomes the representative. One warp per group;
+// 32 members per step, with a prefix sum of their weights and a restart at every vertex that does not fit.
+__global__ void __launch_bounds__(256) k_next_fit(uint32_t cnt, const unsigned long long *sorted, uint32_t *label,
+                                                   int32_t *weight, int32_t max_w) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t p = warp; p < cnt; p += nwarps) {
+    const uint32_t key = static_cast<uint32_t>(sorted[p] >> 32);
+    if (p != 0 && static_cast<uint32_t>(sorted[p - 1] >> 32) == key) {
+      continue; // not a group head (warp-uniform)
+    }
+    uint32_t rep = static_cast<uint32_t>(sorted[p]);
+    int32_t repw = weight[rep];
+    for (uint32_t i = p + 1; i < cnt; i += 32) {
+      const uint32_t idx = i + lane;
+      const bool valid = idx < cnt && static_cast<uint32_t>(sorted[idx] >> 32) == key;
+      const int nvalid = __popc(__ballot_sync(kFull, valid)); // members are contiguous: a prefix of the lanes
+      if (nvalid == 0) {
+        break;
+      }
+      const uint32_t u = valid ? static_cast<uint32_t>(sorted[idx]) : 0u;
+      const int32_t w = valid ? weight[u] : 0;
+      int start = 0;
+      while (start < nvalid) {
+        int32_t pre = (lane >= start && lane < nvalid) ? w : 0; // inclusive prefix over lanes >= start
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t t = __shfl_up_sync(kFull, pre, o);
+          if (lane >= o) {
+            pre += t;
+          }
+        }
+        const bool over = lane >= start && lane < nvalid && (repw + pre > max_w);
+        const unsigned nf = __ballot_sync(kFull, over);
+        const int f = nf != 0 ? __ffs(nf) - 1 : nvalid; // first member that does not fit
+        if (lane >= start && lane < f) {
+          label[u] = rep;
+          weight[u] = 0;
+        }
+        if (f > start) {
+          repw += __shfl_sync(kFull, pre, f - 1);
+        }
+        if (f < nvalid) { // lane f starts a new cluster
+          if (lane == 0) {
+            weight[rep] = repw;
+          }
+          rep = __shfl_sync(kFull, u, f);
+          repw = __shfl_sync(kFull, w, f);
+          start = f + 1;
+        } else {
+          start = nvalid;
+        }
+      }
+      if (nvalid < 32) {
+        break;
+      }
+    }
+    if (lane == 0) {
+      weight[rep] = repw;
+    }
+  }
+}
+
 struct MaxOp {
   __host__ __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
@@ -1526,24 +1592,34 @@ int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, 
   const uint32_t n = h->n;
   const bool two_hop = (1.0 - 1.0 * num_clusters / n) <= h->cfg.two_hop_threshold; // lp_clusterer.cc:164-166
   const int iso = h->cfg.isolated_nodes_strategy;
-  // the CLUSTER variants are refused at kmp_lp_create
-  const bool do_iso = iso == KMP_ISOLATED_MATCH || (iso == KMP_ISOLATED_MATCH_DURING_TWO_HOP && two_hop);
-  if (do_iso && h->num_isolated > 1) {
-    KMP_CUDA(h->pairs_a.ensure(h->num_isolated)); // reuse as u32 storage
+  const bool iso_match = iso == KMP_ISOLATED_MATCH || (iso == KMP_ISOLATED_MATCH_DURING_TWO_HOP && two_hop);
+  const bool iso_cluster = iso == KMP_ISOLATED_CLUSTER || (iso == KMP_ISOLATED_CLUSTER_DURING_TWO_HOP && two_hop);
+  auto sort_pairs = [&](uint32_t cnt, int bits) -> int { // pairs_a -> pairs_b, ascending
+    size_t tmp = 0;
+    KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0, bits, h->stream));
+    KMP_CUDA(h->cub_tmp.ensure(tmp));
+    KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0, bits,
+                                            h->stream));
+    return KMP_OK;
+  };
+  if ((iso_match || iso_cluster) && h->num_isolated > 1) {
+    KMP_CUDA(h->pairs_a.ensure(h->num_isolated));
     KMP_CUDA(h->pairs_b.ensure(h->num_isolated));
-    uint32_t *iso_in = reinterpret_cast<uint32_t *>(h->pairs_a.p);
-    uint32_t *iso_out = reinterpret_cast<uint32_t *>(h->pairs_b.p);
     reset_u32<<<1, 1, 0, h->stream>>>(h->ctr32.p + 2);
-    k_collect_isolated<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, iso_in, h->ctr32.p + 2);
+    k_collect_isolated<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, h->pairs_a.p, h->ctr32.p + 2);
     uint32_t iso_cnt = 0;
     KMP_CUDA(cudaMemcpyAsync(&iso_cnt, h->ctr32.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     KMP_CUDA(cudaStreamSynchronize(h->stream));
     if (iso_cnt > 1) {
-      size_t tmp = 0;
-      KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, iso_in, iso_out, static_cast<int>(iso_cnt), 0, 32, h->stream));
-      KMP_CUDA(h->cub_tmp.ensure(tmp));
-      KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp, iso_in, iso_out, static_cast<int>(iso_cnt), 0, 32, h->stream));
-      k_match_isolated<<<grid_for(iso_cnt / 2 + 1, 256), 256, 0, h->stream>>>(iso_cnt, iso_out, h->label.p, h->weight.p, max_w);
+      const int rc = sort_pairs(iso_cnt, 32); // key 0: ascending vertex id
+      if (rc != KMP_OK) {
+        return rc;
+      }
+      if (iso_match) {
+        k_match_isolated<<<grid_for(iso_cnt / 2 + 1, 256), 256, 0, h->stream>>>(iso_cnt, h->pairs_b.p, h->label.p, h->weight.p, max_w);
+      } else {
+        k_next_fit<<<1, 256, 0, h->stream>>>(iso_cnt, h->pairs_b.p, h->label.p, h->weight.p, max_w); // one group
+      }
       h->kernel_launches += 3;
       KMP_CUDA(cudaGetLastError());
     }
@@ -1563,22 +1639,26 @@ int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, 
   KMP_CUDA(cudaMemcpyAsync(&cnt, h->ctr32.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   if (cnt > 1) {
-    size_t tmp = 0;
-    KMP_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0, 64,
-                                            h->stream));
-    KMP_CUDA(h->cub_tmp.ensure(tmp));
-    KMP_CUDA(cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tmp, h->pairs_a.p, h->pairs_b.p, static_cast<int>(cnt), 0,
-                                            64, h->stream));
-    // group heads: reuse mv-independent scratch (pairs_a is free after the sort)
-    uint32_t *head_in = reinterpret_cast<uint32_t *>(h->pairs_a.p);
-    uint32_t *head_out = head_in + cnt;
-    k_two_hop_heads<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_in);
-    size_t tmp2 = 0;
-    KMP_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
-    KMP_CUDA(h->cub_tmp.ensure(tmp2));
-    KMP_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
-    k_match_two_hop<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_out, h->label.p, h->weight.p);
-    h->kernel_launches += 5;
+    const int rc = sort_pairs(cnt, 64);
+    if (rc != KMP_OK) {
+      return rc;
+    }
+    if (h->cfg.two_hop_strategy == KMP_TWO_HOP_CLUSTER_THREADWISE) {
+      k_next_fit<<<grid_for(static_cast<uint64_t>(cnt) * 32, 256, kSMs * 8), 256, 0, h->stream>>>(cnt, h->pairs_b.p, h->label.p,
+                                                                                                 h->weight.p, max_w);
+      h->kernel_launches += 3;
+    } else {
+      // group heads: reuse mv-independent scratch (pairs_a is free after the sort)
+      uint32_t *head_in = reinterpret_cast<uint32_t *>(h->pairs_a.p);
+      uint32_t *head_out = head_in + cnt;
+      k_two_hop_heads<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_in);
+      size_t tmp2 = 0;
+      KMP_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
+      KMP_CUDA(h->cub_tmp.ensure(tmp2));
+      KMP_CUDA(cub::DeviceScan::InclusiveScan(h->cub_tmp.p, tmp2, head_in, head_out, MaxOp(), static_cast<int>(cnt), h->stream));
+      k_match_two_hop<<<grid_for(cnt, 256), 256, 0, h->stream>>>(cnt, h->pairs_b.p, head_out, h->label.p, h->weight.p);
+      h->kernel_launches += 5;
+    }
     KMP_CUDA(cudaGetLastError());
   }
   return KMP_OK;
@@ -1816,11 +1896,7 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
       return fail(KMP_ERR_UNSUPPORTED, "global two-hop MATCH / CLUSTER (label_propagation.h:1030-1191) is an id-ordered "
                                        "chain: use MATCH_THREADWISE or KMP_SCHEDULE_SEQ_STRICT");
     }
-    if (cfg->two_hop_strategy == KMP_TWO_HOP_CLUSTER_THREADWISE || cfg->isolated_nodes_strategy == KMP_ISOLATED_CLUSTER ||
-        cfg->isolated_nodes_strategy == KMP_ISOLATED_CLUSTER_DURING_TWO_HOP) {
-      return fail(KMP_ERR_UNSUPPORTED, "the CLUSTER post passes (next-fit packing in id order, label_propagation.h:884-1016) "
-                                       "are only implemented by KMP_SCHEDULE_SEQ_STRICT; the sync schedule has the MATCH variants");
-    }
+
   }
   if (cfg->relabel_before_second_phase != 0) { // default false (presets.cc:147)
     return fail(KMP_ERR_UNSUPPORTED, "relabel_before_second_phase (label_propagation.h:272-319) is not implemented");

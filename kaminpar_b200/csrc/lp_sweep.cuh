@@ -580,18 +580,28 @@ template <> struct TeamVals<true> {
   static __device__ __forceinline__ void clear(word *v, uint32_t slot) { reinterpret_cast<uint16_t *>(v)[slot] = 0; }
 };
 
-template <bool V16>
+// With unit edge weights (EW = false) the thread whose CAS claims a slot does NOT add its 1: the stored count is
+// "occurrences beyond the first" and readers add 1 (team_rating). Neighbourhoods are mostly label-distinct, so
+// this halves the shared-memory atomics per edge.
+template <bool V16, bool EW>
 __device__ __forceinline__ void team_table_add(uint32_t *keys, typename TeamVals<V16>::word *vals, uint32_t mask,
                                                bool direct, uint32_t key, int32_t w) {
   uint32_t slot = direct ? key : (lowbias32(key) & mask);
   while (true) {
     const uint32_t prev = atomicCAS(&keys[slot], kEmpty, key);
+    if (!EW && prev == kEmpty) {
+      return;
+    }
     if (prev == kEmpty || prev == key) {
       TeamVals<V16>::add(vals, slot, w);
       return;
     }
     slot = (slot + 1) & mask;
   }
+}
+template <bool V16, bool EW>
+__device__ __forceinline__ int32_t team_rating(const typename TeamVals<V16>::word *vals, uint32_t slot) {
+  return TeamVals<V16>::get(vals, slot) + (EW ? 0 : 1);
 }
 
 template <int MODE, bool EW, bool P64, int T, int SLOTS, int TEAMS, bool V16 = false>
@@ -685,7 +695,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
 #pragma unroll
       for (int j = 0; j < B; ++j) {
         if (kb[j] != kEmpty) {
-          team_table_add<V16>(keys, vals, mask, direct, kb[j], wb[j]);
+          team_table_add<V16, EW>(keys, vals, mask, direct, kb[j], wb[j]);
         }
       }
     }
@@ -701,7 +711,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
         for (uint32_t s = tid; s < cap; s += T) {
           const uint32_t k = keys[s];
           if (k != kEmpty) {
-            const int32_t r = TV::get(vals, s);
+            const int32_t r = team_rating<V16, EW>(vals, s);
             // an entry rated below the thread's running maximum cannot win: its tie hashes are never computed
             // (most entries of a late-round neighbourhood have rating 1 next to a few heavy clusters)
             if (r >= c.gain) {
@@ -741,7 +751,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
             for (int j = 0; j < 4; ++j) {
               const uint32_t s = s0 + j * T + tid;
               kk[j] = s < cap ? keys[s] : kEmpty;
-              rr[j] = kk[j] != kEmpty ? TV::get(vals, s) : 0;
+              rr[j] = kk[j] != kEmpty ? team_rating<V16, EW>(vals, s) : 0;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
           const uint32_t k = keys[s];
           if (k != kEmpty) {
             Cand ff;
-            const Cand cc = eval_candidate_w<1>(a, u, own, uw, own_w, k, TV::get(vals, s), a.weight[k], false, ff);
+            const Cand cc = eval_candidate_w<1>(a, u, own, uw, own_w, k, team_rating<V16, EW>(vals, s), a.weight[k], false, ff);
             if (cand_better<1>(cc, c)) {
               c = cc;
             }

@@ -439,6 +439,10 @@ class LPClustering:
         self._graph = None
         self.last_stats: Optional[KmpStats] = None
 
+    def invalidate_graph(self):
+        """The graph object is recognised by identity: call this when its arrays were rewritten in place."""
+        self._graph = None
+
     def set_max_cluster_weight(self, weight: int):
         self._max_cluster_weight = int(weight)
 
@@ -476,6 +480,9 @@ class LabelPropagationRefiner:
 
     def name(self) -> str:
         return "Label Propagation"
+
+    def invalidate_graph(self):
+        self._graph = None
 
     def set_communities(self, communities):
         self._communities = None if communities is None or len(communities) == 0 else np.asarray(communities)

@@ -368,3 +368,23 @@ def test_device_edge_cut_of_a_clustering(name):
     clusterer.set_max_cluster_weight(mcw)
     c = clusterer.compute_clustering(g)
     assert clusterer._handle.edge_cut() == B.oracle_edge_cut(g, c)
+
+
+@pytest.mark.parametrize("ths,iso", [(4, 3), (4, 4), (2, 2), (4, 2), (2, 1)])
+@pytest.mark.parametrize("name", ["star30000", "star_hub", "road60", "with_isolated", "rmat13_w"])
+def test_t1_cluster_post_pass_variants(name, ths, iso):
+    """CLUSTER_THREADWISE two-hop and the CLUSTER isolated-node variants (next-fit packing in id order, the reference's
+    one-thread outcome: label_propagation.h:884-917, :977-1002) == oracle sync, weights never exceed the limit."""
+    g = get_graph(name)
+    ctx, mcw = ctx_for(g, 8, seed=13)
+    ctx.coarsening.clustering.lp.two_hop_strategy = ths
+    ctx.coarsening.clustering.lp.isolated_nodes_strategy = iso
+    clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
+    clusterer.set_max_cluster_weight(mcw)
+    c = clusterer.compute_clustering(g)
+    cp = B.default_cluster_params()
+    cp.two_hop_strategy, cp.isolated_nodes_strategy = ths, iso
+    expect, st = B.oracle_lp_cluster(g, 13, mcw, schedule=B.SYNC, params=cp, return_stats=True)
+    assert np.array_equal(c, expect)
+    assert clusterer.last_stats.two_hop_ran == st[0].two_hop_ran
+    assert H.cluster_weights_ok(g, c, mcw)

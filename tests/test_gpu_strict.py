@@ -78,7 +78,6 @@ def test_sync_schedule_refuses_order_dependent_options():
     restatement: KMP_ERR_UNSUPPORTED under the sync schedule (never silently mapped), accepted by seq_strict."""
     ctx = lp.create_default_context()
     for field, value in (("tie_breaking_strategy", 0), ("two_hop_strategy", 1), ("two_hop_strategy", 3),
-                         ("two_hop_strategy", 4), ("isolated_nodes_strategy", 2), ("isolated_nodes_strategy", 4),
                          ("relabel_before_second_phase", True)):
         c = lp.create_default_context().coarsening
         setattr(c.clustering.lp, field, value)
