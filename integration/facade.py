@@ -4,7 +4,10 @@ This is NOT a re-implementation of the multilevel partitioner. It drives the UNM
 (coarsening loop, contraction, initial partitioning, balancers) compiled by `make -C oracle ref_b200` with the
 B200 label-propagation clusterer / refiner swapped in behind `factories.cc` (integration/).
 The library only exists where the reference sources were available at build time; without it the constructor
-fails loudly -- there is no fallback partitioner."""
+fails loudly -- there is no fallback partitioner.
+
+Lives in integration/ (demo / test infrastructure), NOT in the product package: it loads a build of the reference
+from oracle/_ref/, which nothing under kaminpar_b200/ may do."""
 from __future__ import annotations
 
 import ctypes as C
@@ -13,7 +16,7 @@ from typing import Optional
 
 import numpy as np
 
-from .graph import CSRGraph
+from kaminpar_b200.graph import CSRGraph
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB_B200 = os.path.join(_ROOT, "oracle", "_ref", "libkaminpar_ref_b200.so")

@@ -62,11 +62,11 @@ def test_compute_partition_through_swapped_factories(name, k, cut_bound):
 
 
 def test_python_facade_over_the_integrated_build():
-    """kaminpar_b200.facade.KaMinPar mirrors the reference's facade (kaminpar.h:857-997) on top of the integrated
+    """integration.facade.KaMinPar mirrors the reference's facade (kaminpar.h:857-997) on top of the integrated
     build: copy_graph / set_k / set_uniform_max_block_weights / compute_partition / reseed."""
     if not os.path.exists(LIB_B200):
         pytest.skip("integrated build not available")
-    from kaminpar_b200.facade import KaMinPar
+    from integration.facade import KaMinPar
 
     g = H.load_graph("walshaw_data")
     KaMinPar.reseed(0)
