@@ -208,6 +208,8 @@ struct kmp_lp_handle {
   // the handle's stream, inside kmp_lp_cluster / kmp_lp_refine
   ncclComm_t comm = nullptr;
   DevBuf<uint32_t> dist_send, dist_recv;
+  uint32_t *direct_send = nullptr; // set while the sweeps of a sharded sub-round write into the send buffer
+  uint32_t direct_cap = 0;
   // cooperative single-launch commit of the clusterer (lp_commit.cuh commit_cluster_fused)
   DevBuf<unsigned> grid_bar; // [0] arrivals, [1] generation
   int fused_blocks = 0;      // co-resident CTAs of the fused kernel (0: not available)
@@ -1030,6 +1032,11 @@ SweepArgs make_sweep_args(kmp_lp_handle *h, const RunCtx &rc) {
   a.mv_u = h->mv_u.p;
   a.mv_t = h->mv_t.p;
   a.mover_count = h->ctr32.p + (h->mover_parity ? 3 : 0);
+  if (h->direct_send != nullptr) { // sharded library path: [count, -, -, -, u[cap], t[cap]]
+    a.mover_count = h->direct_send;
+    a.mv_u = h->direct_send + 4;
+    a.mv_t = h->direct_send + 4 + h->direct_cap;
+  }
   a.incoming = h->incoming.p;
   a.hist = h->hist.p;
   a.counters = h->ctr64.p;
@@ -1057,6 +1064,7 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
   c.acc = h->acc.p;
   c.mover_count = h->ctr32.p + (h->mover_parity ? 3 : 0);
   c.next_mover_count = h->ctr32.p + (h->mover_parity ? 0 : 3);
+  c.also_zero = (h->world > 1 && h->comm != nullptr) ? h->dist_send.p : nullptr;
   c.incoming = h->incoming.p;
   c.slotmap = h->slotmap.p;
   c.cslot = h->cslot.p;
@@ -1333,6 +1341,9 @@ void choose_activation(kmp_lp_handle *h, uint32_t iter) {
 int begin_iteration(kmp_lp_handle *h, uint32_t iter) {
   KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
   KMP_CUDA(cudaMemsetAsync(h->queue.p, 0, h->queue.cap * sizeof(uint32_t), h->stream));
+  if (h->world > 1 && h->comm != nullptr && h->dist_send.p != nullptr) {
+    KMP_CUDA(cudaMemsetAsync(h->dist_send.p, 0, sizeof(uint32_t), h->stream)); // proposal counter of the send buffer
+  }
   h->mover_parity = 0;
   choose_activation(h, iter);
   h->pull_rounds += h->pull_this ? 1 : 0;
@@ -1405,13 +1416,22 @@ int load_nccl() {
 // Sweep this rank's share of sub-round sg and pack its proposals into d_send (4 + 2 * cap words:
 // [count, -, -, -, u[cap], t[cap]]).
 int dist_sweep_pack(kmp_lp_handle *h, const RunCtx &rc, uint32_t iter, uint32_t sg, const SubRound &q, uint32_t *d_send) {
+  const uint32_t cap = subround_cap(h, q);
+  // library path: the sweeps write their proposals straight into the send buffer (count in word 0, zeroed by the
+  // previous commit / begin_iteration) -- no pack kernel
+  h->direct_send = (d_send == h->dist_send.p && h->comm != nullptr) ? d_send : nullptr;
+  h->direct_cap = cap;
   h->stepping = true;
   const int r = sweep_subround(h, rc, iter, sg, q);
   h->stepping = false;
+  const bool direct = h->direct_send != nullptr;
+  h->direct_send = nullptr;
   if (r != KMP_OK) {
     return r;
   }
-  const uint32_t cap = subround_cap(h, q);
+  if (direct) {
+    return KMP_OK;
+  }
   k_pack_movers<<<grid_for(cap, 256, kSMs * 4), 256, 0, h->stream>>>(h->mv_u.p, h->mv_t.p,
                                                                       h->ctr32.p + (h->mover_parity ? 3 : 0), cap, d_send);
   ++h->kernel_launches;

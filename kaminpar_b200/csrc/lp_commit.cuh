@@ -31,6 +31,7 @@ struct CommitArgs {
   uint8_t *__restrict__ acc; // 0 rejected/pending, 1 accepted, 2 contended-pending (clusterer)
   const uint32_t *__restrict__ mover_count;
   uint32_t *__restrict__ next_mover_count; // zeroed for the following sub-round
+  uint32_t *__restrict__ also_zero;        // nullable: a second proposal counter to zero (sharded run: send buffer)
   uint32_t base_commit;
   // clusterer
   int32_t *__restrict__ incoming; // [n]
@@ -201,6 +202,9 @@ __global__ void __launch_bounds__(256) commit_cluster_fused(const CommitArgs a, 
   // ---- apply
   if (tid == 0) {
     *a.next_mover_count = 0;
+    if (a.also_zero != nullptr) {
+      *a.also_zero = 0;
+    }
   }
   uint32_t moved = 0;
   for (uint32_t i = tid; i < cnt; i += nth) {
@@ -527,6 +531,9 @@ __global__ void __launch_bounds__(256) commit_refine_fused(const CommitArgs a, c
   }
   if (tid == 0) {
     *a.next_mover_count = 0;
+    if (a.also_zero != nullptr) {
+      *a.also_zero = 0;
+    }
   }
   for (uint32_t b = tid; b < a.k * kLadderLevels; b += nth) {
     a.hist[b] = 0;
@@ -587,6 +594,9 @@ template <int MODE, bool P64> __global__ void __launch_bounds__(256) commit_appl
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) {
     *a.next_mover_count = 0;
+    if (a.also_zero != nullptr) {
+      *a.also_zero = 0;
+    }
   }
   uint32_t moved = 0;
   for (uint32_t i = tid; i < cnt; i += gridDim.x * blockDim.x) {
