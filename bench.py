@@ -387,7 +387,7 @@ def main():
     sampler.start()
     tot_ms = 0.0
     edges = nodes = launches = sweeps = 0
-    NT = 7  # kernel tiers (include/kaminpar_b200_lp.h kmp_lp_stats)
+    NT = 8  # kernel tiers (include/kaminpar_b200_lp.h kmp_lp_stats)
     g_edges = [0] * NT
     g_nodes = [0] * NT
     g_ms = [0.0] * NT
@@ -494,8 +494,9 @@ def main():
 
     # ---- roofline of the dominant sweep kernel family -------------------------------------------
     peak, peak_src = peaks()
-    names = ["sweep_thread(deg<8)", "sweep_warp(deg<32)", "sweep_team<32>(deg<256)", "sweep_team<128>(deg<1024)",
-             "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<8192)", "sweep_hub_aggregate+partial+final(deg>=8192)"]
+    names = ["sweep_thread<7>(deg<8)", "sweep_thread<15>(deg<16)", "sweep_team<32,64>(deg<32)", "sweep_team<32,512>(deg<256)",
+             "sweep_team<128>(deg<1024)", "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<16384)",
+             "sweep_hub_aggregate+partial+final(deg>=16384)"]
     dom = int(np.argmax(g_ms))
     alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]
     achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0

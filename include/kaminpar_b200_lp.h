@@ -101,13 +101,13 @@ typedef struct {
   float sweep_ms;            /* CUDA-event time spent in the sweep kernels only (if timing enabled) */
   uint64_t sweep_launches;   /* number of sweep-kernel launches */
   uint64_t kernel_launches;  /* all kernel launches of the call */
-  /* per kernel tier (0: deg<8 sweep_thread, 1: deg<32 sweep_warp, 2: deg<256 sweep_team<32>,
-   * 3: deg<1024 sweep_team<128>, 4: deg<4096 sweep_team<512>, 5: deg<8192 sweep_team<1024>,
-   * 6: deg>=8192 sweep_hub_aggregate+partial+final; 7 unused) */
+  /* per kernel tier (0: deg<8 sweep_thread<7>, 1: deg<16 sweep_thread<15>, 2: deg<32 sweep_team<32> (64 slots),
+   * 3: deg<256 sweep_team<32> (512 slots), 4: deg<1024 sweep_team<128>, 5: deg<4096 sweep_team<512>,
+   * 6: deg<8192 / 16384 sweep_team<1024>, 7: above: sweep_hub_aggregate+partial+final) */
   uint64_t group_edges[8];
   uint64_t group_nodes[8];
   uint64_t group_launches[8];
-  float group_sweep_ms[12];  /* only when timing is enabled: [0..6] sweep tiers, [8] commit-rule kernels,
+  float group_sweep_ms[12];  /* only when timing is enabled: [0..7] sweep tiers, [8] commit-rule kernels,
                               * [9] apply, [10] push activation, [11] stamp ageing */
   uint32_t pull_rounds;      /* LP rounds whose sweeps derived the active flags from the move stamps */
   uint32_t push_rounds;      /* LP rounds in which movers flagged their neighbours */

@@ -52,8 +52,8 @@ int fail(int code, const std::string &msg) {
   } while (0)
 
 constexpr int kNumGroups = 4; // degree groups of the schedule
-constexpr int kNumTiers = 7;  // kernel tiers: group 3 (deg >= 256) is split into four tiers
-constexpr int kHubTier = 6;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
+constexpr int kNumTiers = 8;  // kernel tiers: group 1 is split in two, group 3 (deg >= 256) in four
+constexpr int kHubTier = 7;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
 constexpr uint32_t kHubMinDegree = 8192;       // graphs with edge weights (32-bit ratings in the team tables)
 constexpr uint32_t kHubMinDegreeUnit = 16384;  // unit edge weights: 16-bit ratings, twice the slots
 constexpr int kSMs = 148;
@@ -62,9 +62,12 @@ constexpr int kTagCommit = 8, kTagApply = 9, kTagPush = 10, kTagMisc = 11; // ti
 
 // kernel tier of a vertex of degree d >= 1 (tiers 3..6 are degree group 3 of the schedule)
 __host__ __device__ inline uint32_t tier_of(uint32_t d, uint32_t hub_min) {
-  return d < 8 ? 0u : d < 32 ? 1u : d < 256 ? 2u : d < 1024 ? 3u : d < 4096 ? 4u : d < hub_min ? 5u : 6u;
+  return d < 8 ? 0u : d < 16 ? 1u : d < 32 ? 2u : d < 256 ? 3u : d < 1024 ? 4u : d < 4096 ? 5u : d < hub_min ? 6u : 7u;
 }
-inline int group_of_tier(int tier) { return tier < 3 ? tier : 3; }
+// degree groups of the schedule {<8} {<32} {<256} {>=256} and their kernel tiers
+inline int group_of_tier(int tier) { return tier == 0 ? 0 : tier <= 2 ? 1 : tier == 3 ? 2 : 3; }
+inline int first_tier_of_group(int g) { return g == 0 ? 0 : g == 1 ? 1 : g == 2 ? 3 : 4; }
+inline int last_tier_of_group(int g) { return g == 0 ? 0 : g == 1 ? 2 : g == 2 ? 3 : kNumTiers - 1; }
 
 template <typename T> struct DevBuf {
   T *p = nullptr;
@@ -615,6 +618,7 @@ void launch_team(kmp_lp_handle *h, const SweepArgs &a, int ctas_per_sm) {
 
 // dynamic shared memory opt-in of the team kernels (per device; called from kmp_lp_create)
 template <int MODE, bool EW, bool P64> void configure_team_kernels() {
+  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 128, 2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 4 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 512, 8192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
@@ -631,22 +635,25 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
     return cudaSuccess;
   }
   switch (tier) {
-  case 0:
-    sweep_thread<MODE, EW, P64><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
+  case 0: // deg < 8: thread per vertex
+    sweep_thread<MODE, EW, P64, 7><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
     break;
-  case 1:
-    sweep_warp<MODE, EW, P64><<<grid_for(static_cast<uint64_t>((a.list_size + 3) / 4) * 32, 256), 256, 0, h->sweep_stream>>>(a);
+  case 1: // deg < 16: thread per vertex, 15 labels in registers
+    sweep_thread<MODE, EW, P64, 15><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
     break;
-  case 2: // deg < 256: one warp per vertex, 512 slots
+  case 2: // deg < 32: one warp per vertex, 64 slots
+    launch_team<MODE, EW, P64, 32, 64, 8>(h, a, 8);
+    break;
+  case 3: // deg < 256: one warp per vertex, 512 slots
     launch_team<MODE, EW, P64, 32, 512, 8>(h, a, 7);
     break;
-  case 3: // deg < 1024: 128 threads per vertex, 2048 slots
+  case 4: // deg < 1024: 128 threads per vertex, 2048 slots
     launch_team<MODE, EW, P64, 128, 2048, 4>(h, a, 3);
     break;
-  case 4: // deg < 4096: 512 threads per vertex, 8192 slots
+  case 5: // deg < 4096: 512 threads per vertex, 8192 slots
     launch_team<MODE, EW, P64, 512, 8192, 1>(h, a, 3);
     break;
-  case 5: // 1024 threads per vertex; deg < 8192: 16384 slots, or (unit edge weights) deg < 16384: 32768 slots
+  case 6: // 1024 threads per vertex; deg < 8192: 16384 slots, or (unit edge weights) deg < 16384: 32768 slots
     if constexpr (EW) {
       launch_team<MODE, EW, P64, 1024, 16384, 1>(h, a, 1);
     } else {
@@ -826,14 +833,13 @@ int ensure_lists(kmp_lp_handle *h) {
   h->max_list = 0;
   h->mover_cap = 1;
   for (uint32_t sr = 0; sr < S; ++sr) {
-    for (uint32_t t = 0; t < 3; ++t) {
-      h->mover_cap = std::max(h->mover_cap, lsize(t, sr));
+    for (int g = 0; g < kNumGroups; ++g) { // the tiers of a degree group share a sub-round
+      uint32_t tot = 0;
+      for (int t = first_tier_of_group(g); t <= last_tier_of_group(g); ++t) {
+        tot += lsize(static_cast<uint32_t>(t), sr);
+      }
+      h->mover_cap = std::max(h->mover_cap, tot);
     }
-    uint32_t g3 = 0; // the tiers of degree group 3 share a sub-round
-    for (uint32_t t = 3; t < kNumTiers; ++t) {
-      g3 += lsize(t, sr);
-    }
-    h->mover_cap = std::max(h->mover_cap, g3);
   }
   KMP_CUDA(h->queue.ensure(static_cast<size_t>(kNumTiers) * kNumGroups * S));
   h->max_list = h->mover_cap;
@@ -1095,8 +1101,8 @@ SubRound subround_of_sg(const kmp_lp_handle *h, uint32_t sg) {
   SubRound q{};
   q.group = static_cast<int>(sg / S);
   q.sr = sg % S;
-  q.first_tier = q.group < 3 ? q.group : 3;
-  q.last_tier = q.group < 3 ? q.group : kNumTiers - 1;
+  q.first_tier = first_tier_of_group(q.group);
+  q.last_tier = last_tier_of_group(q.group);
   for (int t = q.first_tier; t <= q.last_tier; ++t) {
     const uint32_t sz = h->list_off[t * S + q.sr + 1] - h->list_off[t * S + q.sr];
     q.size[t] = sz;

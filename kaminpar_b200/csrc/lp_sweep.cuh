@@ -1,15 +1,16 @@
 // The LP sweep kernels: one kernel family per degree group of the sync schedule.
 //
-//   tier 0 (deg 1..7)      sweep_thread : one thread per vertex, neighbour labels in registers
-//   tier 1 (deg 8..31)     sweep_warp   : one warp per vertex, duplicates merged with match.any
-//   tier 2 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512-slot shared-memory hash map
-//   tier 3 (deg 256..1023) sweep_team<T=128>  : 128 threads per vertex, 2048 slots
-//   tier 4 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
-//   tier 5 (deg 4096..8191, or ..16383 with unit edge weights: 16-bit ratings) sweep_team<T=1024>: one
+//   tier 0 (deg 1..7)      sweep_thread<D=7>  : one thread per vertex, neighbour labels in registers
+//   tier 1 (deg 8..15)     sweep_thread<D=15> : the same with 15 labels
+//   tier 2 (deg 16..31)    sweep_team<T=32>   : one warp per vertex, 64-slot shared-memory hash map
+//   tier 3 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512 slots
+//   tier 4 (deg 256..1023) sweep_team<T=128>  : 128 threads per vertex, 2048 slots
+//   tier 5 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
+//   tier 6 (deg 4096..8191, or ..16383 with unit edge weights: 16-bit ratings) sweep_team<T=1024>: one
 //                          1024-thread CTA per vertex, 16384 / 32768 slots
-//   tier 6 (deg >= 8192 / 16384)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
+//   tier 7 (deg >= 8192 / 16384)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
 //                          2048-edge chunks, ratings merged into a global table region per vertex
-//   (tiers 3..6 together are degree group 3 of the schedule)
+//   (tiers 1-2 are degree group 1 of the schedule, tiers 4..7 degree group 3)
 //
 // Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
 // rating[label[v]] += w(u,v) over adj(u) (:487-505), clear active[u] (:507-508), select
@@ -58,10 +59,12 @@ __device__ __forceinline__ typename LabG<P64>::word load_labg(const SweepArgs &a
 }
 
 // ================================================================================================
-// tier 0: thread per vertex, deg <= 7
+// tiers 0 and 1: thread per vertex, deg <= D (D = 7 and 15): labels in registers, duplicates merged by an
+// all-pairs compare. Per vertex this costs a few hundred thread instructions -- an order of magnitude fewer
+// issue slots than a warp-wide kernel spends on a 10-neighbour vertex, and consecutive list entries have
+// consecutive adjacency rows, so the per-thread row reads coalesce across the warp.
 // ================================================================================================
-template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
-  constexpr int D = 7;
+template <int MODE, bool EW, bool P64, int D> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
   __shared__ uint32_t s_cnt[2][8]; // proposals per warp of the running CTA iteration (parity-double-buffered)
   __shared__ uint32_t s_base[2];
   unsigned long long edges = 0, nodes = 0;
@@ -216,211 +219,6 @@ template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sw
         idx += s_cnt[par][w];
       }
       emit_proposal<MODE>(a, idx, u, target, uw);
-    }
-  }
-  block_count_flush(a, edges, nodes);
-}
-
-// ================================================================================================
-// tier 1: warp per vertex, deg <= 32, duplicates merged by match.any (no hash table)
-// ================================================================================================
-template <int MODE, bool EW, bool P64> __global__ void __launch_bounds__(256) sweep_warp(const SweepArgs a) {
-  // V vertices per warp and loop iteration: all loads of a stage (vertex record; neighbour id; neighbour
-  // label) are issued for the V vertices before any of them is consumed, so a warp keeps V dependent
-  // load chains in flight instead of one.
-  constexpr int V = 4;
-  // proposals of one CTA iteration (8 warps x V vertices) reserve their slots with ONE atomic on the
-  // proposal counter: on low-degree graphs (RGG, road, grid) nearly every vertex proposes in round 0 and a
-  // per-vertex atomic on that single address serialises in L2
-  __shared__ uint32_t s_cnt[2][8];
-  __shared__ uint32_t s_base[2];
-  unsigned long long edges = 0, nodes = 0;
-  const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t iters = (a.list_size + nwarps * V - 1) / (nwarps * V); // the same for every warp of the grid
-  for (uint32_t it = 0; it < iters; ++it) {
-    const uint32_t i0 = (it * nwarps + warp) * V;
-    bool pr[V];    // lane 0: vertex q proposes a move to pt[q]
-    uint32_t pt[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      pr[q] = false;
-      pt[q] = 0;
-    }
-    uint32_t u[V], beg[V], deg[V], own[V];
-    int32_t uw[V], own_w[V];
-    bool act[V], flag[V], skip[V];
-    // stage 1: vertex records (lane q < V loads vertex q, then broadcast)
-    {
-      uint32_t lu = 0, lbeg = 0, ldeg = 0, lown = 0;
-      int32_t luw = 1, lown_w = 0;
-      int lflag = 0, lvalid = 0;
-      if (lane < V && i0 + lane < a.list_size) {
-        lu = a.list[i0 + lane];
-        lvalid = 1;
-        lflag = a.active == nullptr ? 1 : static_cast<int>(a.active[lu]);
-        lbeg = a.xadj[lu];
-        ldeg = a.xadj[lu + 1] - lbeg;
-        lown = a.label[lu];
-        luw = a.vwgt != nullptr ? a.vwgt[lu] : 1;
-        lown_w = a.weight[lown];
-      }
-#pragma unroll
-      for (int q = 0; q < V; ++q) {
-        u[q] = __shfl_sync(kFull, lu, q);
-        flag[q] = __shfl_sync(kFull, lflag, q) != 0;
-        act[q] = __shfl_sync(kFull, lvalid, q) != 0 && (flag[q] || a.pull); // scanned; decided below
-        beg[q] = __shfl_sync(kFull, lbeg, q);
-        deg[q] = __shfl_sync(kFull, ldeg, q);
-        own[q] = __shfl_sync(kFull, lown, q);
-        uw[q] = __shfl_sync(kFull, luw, q);
-        own_w[q] = __shfl_sync(kFull, lown_w, q);
-        if (deg[q] > a.max_num_neighbors) {
-          deg[q] = a.max_num_neighbors;
-        }
-        skip[q] = false;
-        if (MODE == 1 && act[q]) {
-          const int32_t mn = a.min_w != nullptr ? a.min_w[own[q]] : 0;
-          skip[q] = (own_w[q] - uw[q]) < mn;
-        }
-      }
-    }
-    // stage 2: neighbour ids, stage 3: neighbour labels
-    uint32_t v[V], key[V];
-    int32_t w[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      v[q] = kEmpty;
-      w[q] = 0;
-      if (act[q] && static_cast<uint32_t>(lane) < deg[q]) {
-        v[q] = a.adjncy[beg[q] + lane];
-        w[q] = EW ? a.adjwgt[beg[q] + lane] : 1;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      key[q] = kEmpty;
-      bool hit = false;
-      if (v[q] != kEmpty) {
-        const typename LabG<P64>::word g = load_labg<P64>(a, v[q]);
-        hit = stamp_hit(LabG<P64>::stamp(g), a.window);
-        bool ok = !skip[q];
-        if (MODE == 1 && a.communities != nullptr) {
-          ok = ok && a.communities[u[q]] == a.communities[v[q]];
-        }
-        if (ok) {
-          key[q] = LabG<P64>::label(g);
-        }
-      }
-      if (act[q] && !flag[q]) { // pull: active iff a neighbour moved since the last visit
-        act[q] = __any_sync(kFull, hit);
-      }
-    }
-    // stage 4: ratings by match.any, candidate weights gathered for all V vertices before evaluation
-    int32_t rating[V], kw[V];
-    bool rep[V];
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      const unsigned peers = __match_any_sync(kFull, key[q]);
-      if (EW) {
-        rating[q] = 0;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int32_t wt = __shfl_sync(kFull, w[q], t);
-          rating[q] += ((peers >> t) & 1u) ? wt : 0;
-        }
-      } else {
-        rating[q] = __popc(peers);
-      }
-      rep[q] = act[q] && (key[q] != kEmpty) && (lane == __ffs(peers) - 1);
-      kw[q] = (MODE == 1 && rep[q]) ? a.weight[key[q]] : 0; // clusterer: gathered lazily below
-    }
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      if (!act[q]) {
-        continue; // warp-uniform
-      }
-      const bool store_fav = (MODE == 0) && (uw[q] == own_w[q]) && (own_w[q] <= a.max_cluster_weight / 2);
-      Cand c = cand_none(), f = cand_none();
-      Cand best, fav = cand_none();
-      if (MODE == 0) {
-        // rank without the cluster weights; only the top candidate's weight is loaded (one broadcast load).
-        // If that cluster is full, every candidate is evaluated with its weight.
-        if (rep[q] && rating[q] > 0) {
-          c = Cand{rating[q], 0, tie_hash(a.base_tie, u[q], key[q]), key[q]};
-          if (store_fav) {
-            f = Cand{rating[q], 0, tie_hash(a.base_fav, u[q], key[q]), key[q]};
-          }
-        }
-        const Cand top = warp_argmax<0>(kFull, c);
-        if (store_fav) {
-          fav = warp_argmax<0>(kFull, f);
-        }
-        bool top_ok = true;
-        if (top.gain > 0) {
-          top_ok = (a.weight[top.key] + uw[q] <= a.max_cluster_weight) || (top.key == own[q]);
-          if (a.communities != nullptr) {
-            top_ok = top_ok && (a.communities[top.key] == a.communities[own[q]]);
-          }
-        }
-        if (top_ok) {
-          best = top;
-        } else {
-          Cand cf = cand_none(), ff;
-          if (rep[q]) {
-            cf = eval_candidate_w<0>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], a.weight[key[q]], false, ff);
-          }
-          best = warp_argmax<0>(kFull, cf);
-        }
-      } else {
-        if (rep[q]) {
-          c = eval_candidate_w<MODE>(a, u[q], own[q], uw[q], own_w[q], key[q], rating[q], kw[q], store_fav, f);
-        }
-        best = warp_argmax<MODE>(kFull, c);
-      }
-      if (lane == 0) {
-        edges += deg[q];
-        nodes += 1;
-        if (a.active != nullptr && flag[q]) {
-          a.active[u[q]] = 0;
-        }
-        uint32_t target;
-        pr[q] = finish_vertex<MODE>(a, u[q], own[q], store_fav, best, fav, target);
-        pt[q] = target;
-      }
-    }
-    uint32_t np = 0;
-#pragma unroll
-    for (int q = 0; q < V; ++q) {
-      np += pr[q] ? 1u : 0u;
-    }
-    // one slot reservation per CTA iteration (parity-double-buffered, two barriers)
-    const int par = it & 1;
-    if (lane == 0) {
-      s_cnt[par][wib] = np;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t total = 0;
-      for (int w = 0; w < 8; ++w) {
-        total += s_cnt[par][w];
-      }
-      s_base[par] = total != 0 ? atomicAdd(a.mover_count, total) : 0u;
-    }
-    __syncthreads();
-    if (lane == 0 && np != 0) {
-      uint32_t idx = s_base[par];
-      for (int w = 0; w < wib; ++w) {
-        idx += s_cnt[par][w];
-      }
-#pragma unroll
-      for (int q = 0; q < V; ++q) {
-        if (pr[q]) {
-          emit_proposal<MODE>(a, idx++, u[q], pt[q], uw[q]);
-        }
-      }
     }
   }
   block_count_flush(a, edges, nodes);
@@ -808,7 +606,7 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
 }
 
 // ================================================================================================
-// tier 6 (deg >= 8192): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
+// tier 7 (deg >= 8192 / 16384): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
 // shared-memory hash map and merges the distinct keys into the vertex's global table region.
 // Phase 2: one CTA per vertex scans its region, selects, and clears it.
 // ================================================================================================
