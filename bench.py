@@ -419,9 +419,9 @@ def main():
             g_nodes[q] += st.group_nodes[q]
             g_ms[q] += st.group_sweep_ms[q]
             g_launch[q] += st.group_launches[q]
-        commit_ms += st.group_sweep_ms[8]
-        apply_ms += st.group_sweep_ms[9]
-        push_ms += st.group_sweep_ms[10]
+        commit_ms += st.group_sweep_ms[12]
+        apply_ms += st.group_sweep_ms[13]
+        push_ms += st.group_sweep_ms[14]
     (refine_handle or handle).set_timing(False)
     barrier()
     t = torch.tensor([tot_ms, float(edges)], dtype=torch.float64, device=dev)
@@ -494,8 +494,8 @@ def main():
 
     # ---- roofline of the dominant sweep kernel family -------------------------------------------
     peak, peak_src = peaks()
-    names = ["sweep_thread<7>(deg<8)", "sweep_thread<15>(deg<16)", "sweep_team<32,64>(deg<32)", "sweep_team<32,512>(deg<256)",
-             "sweep_team<128>(deg<1024)", "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<16384)",
+    names = ["sweep_thread<8>(deg<8)", "sweep_thread<16>(deg<=16)", "sweep_thread<32>(deg<32)",
+             "sweep_team<32>(deg<256)", "sweep_team<128>(deg<1024)", "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<16384)",
              "sweep_hub_aggregate+partial+final(deg>=16384)"]
     dom = int(np.argmax(g_ms))
     alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]

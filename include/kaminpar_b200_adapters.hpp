@@ -98,7 +98,14 @@ inline void check(int rc) {
 }
 class Handle {
 public:
-  explicit Handle(const kmp_lp_config &cfg) { check(kmp_lp_create(&cfg, &_h)); }
+  explicit Handle(const kmp_lp_config &cfg) {
+    // struct layouts (kmp_lp_config / kmp_lp_stats) are part of the ABI: refuse a library built from another header
+    if (kmp_lp_abi_version() != KMP_LP_ABI_VERSION) {
+      throw std::runtime_error("kaminpar_b200: library ABI version " + std::to_string(kmp_lp_abi_version()) +
+                               " != header ABI version " + std::to_string(KMP_LP_ABI_VERSION));
+    }
+    check(kmp_lp_create(&cfg, &_h));
+  }
   Handle(const Handle &) = delete;
   Handle &operator=(const Handle &) = delete;
   ~Handle() { kmp_lp_destroy(_h); }

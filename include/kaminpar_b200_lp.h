@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define KMP_LP_ABI_VERSION 2
+#define KMP_LP_ABI_VERSION 3
 
 typedef enum {
   KMP_OK = 0,
@@ -101,14 +101,14 @@ typedef struct {
   float sweep_ms;            /* CUDA-event time spent in the sweep kernels only (if timing enabled) */
   uint64_t sweep_launches;   /* number of sweep-kernel launches */
   uint64_t kernel_launches;  /* all kernel launches of the call */
-  /* per kernel tier (0: deg<8 sweep_thread<7>, 1: deg<16 sweep_thread<15>, 2: deg<32 sweep_team<32> (64 slots),
-   * 3: deg<256 sweep_team<32> (512 slots), 4: deg<1024 sweep_team<128>, 5: deg<4096 sweep_team<512>,
-   * 6: deg<8192 / 16384 sweep_team<1024>, 7: above: sweep_hub_aggregate+partial+final) */
-  uint64_t group_edges[8];
-  uint64_t group_nodes[8];
-  uint64_t group_launches[8];
-  float group_sweep_ms[12];  /* only when timing is enabled: [0..7] sweep tiers, [8] commit-rule kernels,
-                              * [9] apply, [10] push activation, [11] stamp ageing */
+  /* per kernel tier (8 in use: 0: deg<=7 sweep_thread<8>, 1: deg<=16 sweep_thread<16>, 2: deg<=31 sweep_thread<32>,
+   * 3: deg<256 sweep_team<32>, 4: deg<1024 sweep_team<128>, 5: deg<4096 sweep_team<512>, 6: deg<8192 / 16384
+   * sweep_team<1024>, 7: above: sweep_hub_aggregate+partial+final; slots 8..11 are reserved) */
+  uint64_t group_edges[12];
+  uint64_t group_nodes[12];
+  uint64_t group_launches[12];
+  float group_sweep_ms[16];  /* only when timing is enabled: [0..11] sweep tiers, [12] commit-rule kernels,
+                              * [13] apply, [14] push activation, [15] stamp ageing */
   uint32_t pull_rounds;      /* LP rounds whose sweeps derived the active flags from the move stamps */
   uint32_t push_rounds;      /* LP rounds in which movers flagged their neighbours */
 } kmp_lp_stats;

@@ -54,15 +54,17 @@ int fail(int code, const std::string &msg) {
 constexpr int kNumGroups = 4; // degree groups of the schedule
 constexpr int kNumTiers = 8;  // kernel tiers: group 1 is split in two, group 3 (deg >= 256) in four
 constexpr int kHubTier = 7;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
+constexpr int kStatTiers = 12; // tier slots of kmp_lp_stats / ctr64 (edges at [tier], nodes at [kCtrNodes + tier])
+constexpr int kCtrNodes = 16, kCtrScratch = 40, kCtrSize = 48;
 constexpr uint32_t kHubMinDegree = 8192;       // graphs with edge weights (32-bit ratings in the team tables)
 constexpr uint32_t kHubMinDegreeUnit = 16384;  // unit edge weights: 16-bit ratings, twice the slots
 constexpr int kSMs = 148;
 constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512)
-constexpr int kTagCommit = 8, kTagApply = 9, kTagPush = 10, kTagMisc = 11; // timing slots besides the tiers
+constexpr int kTagCommit = 12, kTagApply = 13, kTagPush = 14, kTagMisc = 15; // timing slots besides the tiers
 
-// kernel tier of a vertex of degree d >= 1 (tiers 3..6 are degree group 3 of the schedule)
+// kernel tier of a vertex of degree d >= 1
 __host__ __device__ inline uint32_t tier_of(uint32_t d, uint32_t hub_min) {
-  return d < 8 ? 0u : d < 16 ? 1u : d < 32 ? 2u : d < 256 ? 3u : d < 1024 ? 4u : d < 4096 ? 5u : d < hub_min ? 6u : 7u;
+  return d < 8 ? 0u : d <= 16 ? 1u : d < 32 ? 2u : d < 256 ? 3u : d < 1024 ? 4u : d < 4096 ? 5u : d < hub_min ? 6u : 7u;
 }
 // degree groups of the schedule {<8} {<32} {<256} {>=256} and their kernel tiers
 inline int group_of_tier(int tier) { return tier == 0 ? 0 : tier <= 2 ? 1 : tier == 3 ? 2 : 3; }
@@ -118,7 +120,8 @@ struct kmp_lp_handle {
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_events;
   std::vector<int> sweep_event_group;
-  uint64_t group_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t group_launches[kStatTiers] = {};
+  uint32_t thread_max_deg = 32; // KMP_THREAD_MAX_DEG: 16 / 32 (which tiers run the register-sort kernel)
   // packed (label, stamp) gather array of the sweeps (lp_device.cuh): 4 B per vertex while labels fit 24 bits
   // (n <= 2^24 clusterer / k <= 2^24 refiner), else 8 B
   DevBuf<unsigned char> labg;
@@ -618,7 +621,6 @@ void launch_team(kmp_lp_handle *h, const SweepArgs &a, int ctas_per_sm) {
 
 // dynamic shared memory opt-in of the team kernels (per device; called from kmp_lp_create)
 template <int MODE, bool EW, bool P64> void configure_team_kernels() {
-  cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 128, 2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 4 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 512, 8192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
@@ -634,17 +636,22 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
   if (a.list_size == 0) {
     return cudaSuccess;
   }
+  const uint32_t tgrid = grid_for(a.list_size, 256);
   switch (tier) {
-  case 0: // deg < 8: thread per vertex
-    sweep_thread<MODE, EW, P64, 7><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
+  case 0: // deg <= 7: thread per vertex, labels sorted in registers
+    sweep_thread<MODE, EW, P64, 8><<<tgrid, 256, 0, h->sweep_stream>>>(a);
     break;
-  case 1: // deg < 16: thread per vertex, 15 labels in registers
-    sweep_thread<MODE, EW, P64, 15><<<grid_for(a.list_size, 256), 256, 0, h->sweep_stream>>>(a);
+  case 1: // deg 8..16
+    sweep_thread<MODE, EW, P64, 16><<<tgrid, 256, 0, h->sweep_stream>>>(a);
     break;
-  case 2: // deg < 32: one warp per vertex, 64 slots
-    launch_team<MODE, EW, P64, 32, 64, 8>(h, a, 8);
+  case 2: // deg 17..31 (KMP_THREAD_MAX_DEG=16 sends them to the warp-team kernel instead: experiments)
+    if (h->thread_max_deg >= 32) {
+      sweep_thread<MODE, EW, P64, 32><<<tgrid, 256, 0, h->sweep_stream>>>(a);
+    } else {
+      launch_team<MODE, EW, P64, 32, 512, 8>(h, a, 7);
+    }
     break;
-  case 3: // deg < 256: one warp per vertex, 512 slots
+  case 3: // deg 32..255: one warp per vertex, 512 slots (a 64-register sort was measured: 1.5-2x slower here)
     launch_team<MODE, EW, P64, 32, 512, 8>(h, a, 7);
     break;
   case 4: // deg < 1024: 128 threads per vertex, 2048 slots
@@ -727,7 +734,7 @@ void timed_end(kmp_lp_handle *h, int idx, cudaStream_t st = nullptr) {
   }
 }
 
-// tier: kernel tier 0..6 of the list in `a_in`
+// tier: kernel tier 0..kNumTiers-1 of the list in `a_in`
 cudaError_t launch_sweep(kmp_lp_handle *h, int mode, int tier, const SweepArgs &a_in) {
   if (a_in.list_size == 0) {
     return cudaSuccess;
@@ -972,7 +979,7 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
   KMP_CUDA(h->mv_t.ensure(cap));
   KMP_CUDA(h->acc.ensure(cap));
   KMP_CUDA(h->ctr32.ensure(512));
-  KMP_CUDA(h->ctr64.ensure(32));
+  KMP_CUDA(h->ctr64.ensure(kCtrSize));
   KMP_CUDA(h->active.ensure(h->n));
   if (mode == 0) {
     KMP_CUDA(h->cslot.ensure(cap));
@@ -1560,7 +1567,7 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   h->sweep_launches = 0;
   h->pull_rounds = h->push_rounds = 0;
   h->sweep_events_used = 0;
-  for (int g = 0; g < 8; ++g) {
+  for (int g = 0; g < kStatTiers; ++g) {
     h->group_launches[g] = 0;
   }
   KMP_CUDA(cudaEventRecord(h->ev_begin, h->stream));
@@ -1569,19 +1576,19 @@ int begin_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
 
 int end_call(kmp_lp_handle *h, kmp_lp_stats *stats) {
   if (h->world > 1 && h->comm != nullptr && stats != nullptr) { // every rank reports the whole job's scan counters
-    KMP_NCCL(g_nccl.AllReduce(h->ctr64.p, h->ctr64.p, 16, ncclUint64, ncclSum, h->comm, h->stream));
+    KMP_NCCL(g_nccl.AllReduce(h->ctr64.p, h->ctr64.p, kCtrNodes + kStatTiers, ncclUint64, ncclSum, h->comm, h->stream));
   }
   KMP_CUDA(cudaEventRecord(h->ev_end, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   if (stats != nullptr) {
-    unsigned long long c[16] = {0};
+    unsigned long long c[kCtrNodes + kStatTiers] = {0};
     KMP_CUDA(cudaMemcpy(c, h->ctr64.p, sizeof(c), cudaMemcpyDeviceToHost));
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < kStatTiers; ++g) {
       stats->group_edges[g] = c[g];
-      stats->group_nodes[g] = c[8 + g];
+      stats->group_nodes[g] = c[kCtrNodes + g];
       stats->group_launches[g] = h->group_launches[g];
       stats->edges_scanned += c[g];
-      stats->nodes_visited += c[8 + g];
+      stats->nodes_visited += c[kCtrNodes + g];
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end);
@@ -1692,7 +1699,7 @@ int cluster_post_passes(kmp_lp_handle *h, int32_t max_w, uint32_t num_clusters, 
 
 // ---- schedule KMP_SCHEDULE_SEQ_STRICT ----------------------------------------------------------------
 // mode 0: labels are (re)initialised by the engine; mode 1: h->label holds the partition. Results stay in
-// h->label / h->weight; iteration statistics go to *stats, the scan counters to tier slot 7 of ctr64.
+// h->label / h->weight; iteration statistics go to *stats, the scan counters to the last tier slot of ctr64.
 int run_strict(kmp_lp_handle *h, int mode, uint32_t num_keys, int32_t max_cluster_weight, uint32_t desired,
                uint32_t k, bool has_min, bool has_comm, kmp_lp_stats *stats) {
   const size_t n = std::max<uint32_t>(h->n, 1);
@@ -1781,8 +1788,8 @@ int run_strict(kmp_lp_handle *h, int mode, uint32_t num_keys, int32_t max_cluste
   }
   // end_call sums the per-tier scan counters: park the engine's totals in tier slot 7
   unsigned long long c[2] = {hs.edges_scanned, hs.nodes_visited};
-  KMP_CUDA(cudaMemcpy(h->ctr64.p + 7, &c[0], 8, cudaMemcpyHostToDevice));
-  KMP_CUDA(cudaMemcpy(h->ctr64.p + 15, &c[1], 8, cudaMemcpyHostToDevice));
+  KMP_CUDA(cudaMemcpy(h->ctr64.p + (kStatTiers - 1), &c[0], 8, cudaMemcpyHostToDevice));
+  KMP_CUDA(cudaMemcpy(h->ctr64.p + kCtrNodes + (kStatTiers - 1), &c[1], 8, cudaMemcpyHostToDevice));
   return KMP_OK;
 }
 
@@ -1793,8 +1800,8 @@ int strict_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   const uint32_t n = h->n;
   KMP_CUDA(h->label.ensure(std::max<uint32_t>(n, 1)));
   KMP_CUDA(h->weight.ensure(std::max<uint32_t>(n, 1)));
-  KMP_CUDA(h->ctr64.ensure(32));
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(h->ctr64.ensure(kCtrSize));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   if (communities != nullptr) {
     KMP_CUDA(h->communities.ensure(n));
     KMP_CUDA(cudaMemcpyAsync(h->communities.p, communities, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1825,8 +1832,8 @@ int strict_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   KMP_CUDA(h->label.ensure(std::max<uint32_t>(n, 1)));
   KMP_CUDA(h->weight.ensure(std::max<uint32_t>(std::max(n, k), 1)));
   KMP_CUDA(h->maxw.ensure(k));
-  KMP_CUDA(h->ctr64.ensure(32));
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(h->ctr64.ensure(kCtrSize));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   if (partition_inout != nullptr && n > 0) {
     KMP_CUDA(cudaMemcpyAsync(h->label.p, partition_inout, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, h->stream));
   }
@@ -1939,6 +1946,9 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
   h->cfg = *cfg;
   if (const char *e = std::getenv("KMP_HUB_CAP_PCT")) { // experiment knobs; results do not depend on them
     h->hub_cap_pct = std::max(110, std::atoi(e));
+  }
+  if (const char *e = std::getenv("KMP_THREAD_MAX_DEG")) {
+    h->thread_max_deg = static_cast<uint32_t>(std::max(16, std::atoi(e)));
   }
   if (const char *e = std::getenv("KMP_HUB_WAVE_SLOTS")) {
     h->hub_wave_slots = static_cast<uint64_t>(std::max(32ll, std::atoll(e)));
@@ -2180,7 +2190,7 @@ int kmp_lp_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, uint32_t desire
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   if (n > 0) {
     launch_init_cluster(h);
     ++h->kernel_launches;
@@ -2305,7 +2315,7 @@ int kmp_lp_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_block_weights
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
   if (n > 0) {
     k_block_weights<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->vwgt, h->label.p, h->weight.p);
@@ -2381,7 +2391,7 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
       KMP_CUDA(cudaMemcpyAsync(h->minw.p, min_weights, static_cast<size_t>(num_labels) * 4, cudaMemcpyHostToDevice, h->stream));
     }
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   if (n > 0) {
     launch_pack_labels(h);
   }
@@ -2473,12 +2483,12 @@ int kmp_lp_edge_cut(kmp_lp_handle *h, int64_t *cut_out) {
     return fail(KMP_ERR_INVALID, "bad argument");
   }
   KMP_CUDA(cudaSetDevice(h->device));
-  KMP_CUDA(h->ctr64.ensure(32));
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + 24, 0, sizeof(unsigned long long), h->stream));
+  KMP_CUDA(h->ctr64.ensure(kCtrSize));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p + kCtrScratch, 0, sizeof(unsigned long long), h->stream));
   k_edge_cut<<<grid_for(static_cast<uint64_t>(h->n) * 32, 256), 256, 0, h->stream>>>(h->n, h->xadj, h->adjncy, h->adjwgt,
-                                                                                      h->label.p, h->ctr64.p + 24);
+                                                                                      h->label.p, h->ctr64.p + kCtrScratch);
   unsigned long long c = 0;
-  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + 24, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  KMP_CUDA(cudaMemcpyAsync(&c, h->ctr64.p + kCtrScratch, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
   KMP_CUDA(cudaStreamSynchronize(h->stream));
   *cut_out = static_cast<int64_t>(c / 2); // metrics.cc:51-52
   return KMP_OK;
@@ -2614,7 +2624,7 @@ int kmp_lp_step_begin_cluster(kmp_lp_handle *h, int32_t max_cluster_weight, cons
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   if (n > 0) {
     launch_init_cluster(h);
   }
@@ -2661,7 +2671,7 @@ int kmp_lp_step_begin_refine(kmp_lp_handle *h, uint32_t k, const int32_t *max_bl
   if (rc != KMP_OK) {
     return rc;
   }
-  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, 32 * sizeof(unsigned long long), h->stream));
+  KMP_CUDA(cudaMemsetAsync(h->ctr64.p, 0, kCtrSize * sizeof(unsigned long long), h->stream));
   KMP_CUDA(cudaMemsetAsync(h->weight.p, 0, static_cast<size_t>(k) * 4, h->stream));
   rc = prepare_labg(h, k);
   if (rc != KMP_OK) {

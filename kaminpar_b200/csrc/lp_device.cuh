@@ -154,6 +154,7 @@ __device__ __forceinline__ bool stamp_hit(uint32_t stamp, const StampWindow &w) 
 }
 
 // ---- per-vertex context -------------------------------------------------------------------------
+constexpr int kCounterNodesOffset = 16; // scan counters: edges at [tier], visited vertices at [16 + tier]
 struct SweepArgs {
   // graph
   const uint32_t *__restrict__ xadj;
@@ -187,7 +188,7 @@ struct SweepArgs {
   bool accumulate;                     // add to incoming[] / hist[] while emitting proposals
   int32_t *__restrict__ incoming;      // clusterer: [n]
   int32_t *__restrict__ hist;          // refiner: [k][16]
-  unsigned long long *__restrict__ counters; // [0] edges scanned, [8] nodes visited (of this kernel tier)
+  unsigned long long *__restrict__ counters; // [0] edges scanned, [kCounterNodesOffset] nodes visited (of this kernel tier)
   // select_all mode (T0 parity hook): write decisions instead of proposing
   uint32_t *__restrict__ sel_target;
   uint32_t *__restrict__ sel_favored;

@@ -1,22 +1,23 @@
 // The LP sweep kernels: one kernel family per degree group of the sync schedule.
 //
-//   tier 0 (deg 1..7)      sweep_thread<D=7>  : one thread per vertex, neighbour labels in registers
-//   tier 1 (deg 8..15)     sweep_thread<D=15> : the same with 15 labels
-//   tier 2 (deg 16..31)    sweep_team<T=32>   : one warp per vertex, 64-slot shared-memory hash map
-//   tier 3 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512 slots
+//   tier 0 (deg 1..7)      sweep_thread<N=8>  : one thread per vertex, neighbour labels sorted in registers
+//   tier 1 (deg 8..16)     sweep_thread<N=16>
+//   tier 2 (deg 17..31)    sweep_thread<N=32>
+//   tier 3 (deg 32..255)   sweep_team<T=32>   : one warp per vertex, 512-slot shared-memory hash map
 //   tier 4 (deg 256..1023) sweep_team<T=128>  : 128 threads per vertex, 2048 slots
 //   tier 5 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
 //   tier 6 (deg 4096..8191, or ..16383 with unit edge weights: 16-bit ratings) sweep_team<T=1024>: one
 //                          1024-thread CTA per vertex, 16384 / 32768 slots
-//   tier 7 (deg >= 8192 / 16384)   sweep_hub_aggregate + sweep_hub_partial + sweep_hub_final : edge-parallel over
-//                          2048-edge chunks, ratings merged into a global table region per vertex
-//   (tiers 1-2 are degree group 1 of the schedule, tiers 4..7 degree group 3)
+//   tier 7 (deg >= 8192 / 16384) sweep_hub_*  : edge-parallel chunks, global 64-bit table (see below)
+//   (tiers 1-2 are degree group 1 of the schedule, tiers 4..7 group 3)
 //
 // Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
 // rating[label[v]] += w(u,v) over adj(u) (:487-505), clear active[u] (:507-508), select
 // (lp_clusterer.cc:181-250 / lp_refiner.cc:151-245) and -- instead of moving immediately
 // (try_node_move :817-841) -- emit a proposal (u, target) that the commit kernels resolve.
 #pragma once
+
+#include <utility>
 
 #include "lp_device.cuh"
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ void block_count_flush(const SweepArgs &a, unsigned l
   }
   if ((threadIdx.x & 31) == 0 && nodes != 0) {
     atomicAdd(&a.counters[0], edges); // counters points at this degree group's slot
-    atomicAdd(&a.counters[8], nodes);
+    atomicAdd(&a.counters[kCounterNodesOffset], nodes);
   }
 }
 
@@ -59,12 +60,80 @@ __device__ __forceinline__ typename LabG<P64>::word load_labg(const SweepArgs &a
 }
 
 // ================================================================================================
-// tiers 0 and 1: thread per vertex, deg <= D (D = 7 and 15): labels in registers, duplicates merged by an
-// all-pairs compare. Per vertex this costs a few hundred thread instructions -- an order of magnitude fewer
-// issue slots than a warp-wide kernel spends on a 10-neighbour vertex, and consecutive list entries have
-// consecutive adjacency rows, so the per-thread row reads coalesce across the warp.
+// tiers 0..2: thread per vertex, deg <= N (N = 8, 16, 32). The neighbour labels are gathered into N
+// registers (N independent gathers in flight per thread), sorted there with Batcher's odd-even merge network
+// (fully unrolled: 19 / 63 / 191 compare-exchanges of two instructions each, no divergence -- empty slots
+// hold 0xFFFFFFFF and sort to the end), and the ratings are the run lengths of the sorted sequence. Per vertex this
+// costs a few hundred to ~1500 thread instructions (20-50 per edge) where a warp-wide hash-map kernel spends
+// ~250 per edge (N = 64 was measured too: 230 registers, 1.5-2x slower than the warp kernel on deg 32..64), and consecutive list entries have consecutive adjacency rows, so the per-thread row reads share
+// sectors across the warp.
 // ================================================================================================
-template <int MODE, bool EW, bool P64, int D> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
+template <bool EW>
+__host__ __device__ __forceinline__ void compare_exchange(uint32_t &ka, uint32_t &kb, int32_t &wa, int32_t &wb) {
+  if (EW) {
+    const bool sw = ka > kb;
+    const uint32_t k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const int32_t w0 = sw ? wb : wa, w1 = sw ? wa : wb;
+    ka = k0;
+    kb = k1;
+    wa = w0;
+    wb = w1;
+  } else {
+    const uint32_t lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
+    ka = lo;
+    kb = hi;
+  }
+}
+// The compare-exchange list of Batcher's odd-even merge sort, computed at compile time so that every register
+// index below is a constant (a run-time loop nest would push the arrays into local memory).
+template <int N> struct SortNetwork {
+  static constexpr int kMaxPairs = 576; // N = 64 needs 543
+  int count = 0;
+  unsigned char lo[kMaxPairs] = {}, hi[kMaxPairs] = {};
+};
+template <int N> constexpr SortNetwork<N> make_sort_network() {
+  SortNetwork<N> net{};
+  for (int p = 1; p < N; p <<= 1) {
+    for (int q = p; q >= 1; q >>= 1) {
+      for (int j = q % p; j + q < N; j += 2 * q) {
+        for (int i = 0; i < q; ++i) {
+          if (i + j + q < N && (i + j) / (2 * p) == (i + j + q) / (2 * p)) {
+            net.lo[net.count] = static_cast<unsigned char>(i + j);
+            net.hi[net.count] = static_cast<unsigned char>(i + j + q);
+            ++net.count;
+          }
+        }
+      }
+    }
+  }
+  return net;
+}
+template <int N> struct SortNetworkOf {
+  static constexpr SortNetwork<N> net = make_sort_network<N>();
+};
+template <int N, bool EW, int IDX>
+__host__ __device__ __forceinline__ void sort_step(uint32_t (&k)[N], int32_t (&w)[N]) {
+  if constexpr (IDX < SortNetworkOf<N>::net.count) {
+    constexpr int A = SortNetworkOf<N>::net.lo[IDX];
+    constexpr int B = SortNetworkOf<N>::net.hi[IDX];
+    compare_exchange<EW>(k[A], k[B], w[A], w[B]);
+  }
+}
+template <int N, bool EW, int BASE, int... I>
+__host__ __device__ __forceinline__ void sort_steps(uint32_t (&k)[N], int32_t (&w)[N], std::integer_sequence<int, I...>) {
+  (sort_step<N, EW, BASE + I>(k, w), ...);
+}
+template <int N, bool EW, int... C>
+__host__ __device__ __forceinline__ void sort_chunks(uint32_t (&k)[N], int32_t (&w)[N], std::integer_sequence<int, C...>) {
+  (sort_steps<N, EW, C * 64>(k, w, std::make_integer_sequence<int, 64>{}), ...);
+}
+// ascending by key; the weights travel with their keys (EW only)
+template <int N, bool EW> __host__ __device__ __forceinline__ void sort_registers(uint32_t (&k)[N], int32_t (&w)[N]) {
+  static_assert((N & (N - 1)) == 0 && N <= 64, "network size must be a power of two <= 64");
+  sort_chunks<N, EW>(k, w, std::make_integer_sequence<int, (SortNetworkOf<N>::net.count + 63) / 64>{});
+}
+
+template <int MODE, bool EW, bool P64, int N> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
   __shared__ uint32_t s_cnt[2][8]; // proposals per warp of the running CTA iteration (parity-double-buffered)
   __shared__ uint32_t s_base[2];
   unsigned long long edges = 0, nodes = 0;
@@ -88,11 +157,11 @@ template <int MODE, bool EW, bool P64, int D> __global__ void __launch_bounds__(
         const uint32_t own = a.label[u];
         uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
         const int32_t own_w = a.weight[own];
-        uint32_t keys[D];
-        int32_t ws[D];
+        uint32_t keys[N];
+        int32_t ws[N];
         bool hit = false;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
+        for (int j = 0; j < N; ++j) {
           keys[j] = kEmpty;
           ws[j] = 0;
           if (j < static_cast<int>(deg)) {
@@ -122,71 +191,66 @@ template <int MODE, bool EW, bool P64, int D> __global__ void __launch_bounds__(
           }
           const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
           Cand best = cand_none(), fav = cand_none();
-          bool lazy_done = false;
-          if (MODE == 0 && !skip) {
-            // Clusterer: rank the candidates WITHOUT their cluster weights (one random gather each, DRAM-resident
-            // on large graphs); only the top one is checked. If it is full, fall through to the full evaluation.
-            Cand top = cand_none();
+          if (!skip) {
+            sort_registers<N, EW>(keys, ws);
+            bool lazy_done = false;
+            if (MODE == 0) {
+              // Clusterer: rank the candidates WITHOUT their cluster weights (one random gather each, DRAM-resident
+              // on large graphs); only the top one is checked. If it is full, fall through to the full evaluation.
+              // A run rated below the running maximum cannot win: its tie hashes are never computed.
+              Cand top = cand_none();
+              int32_t run = 0;
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
-              if (keys[j] != kEmpty) {
-                bool first = true;
-                int32_t rating = 0;
-#pragma unroll
-                for (int q = 0; q < D; ++q) {
-                  const bool same = keys[q] == keys[j];
-                  rating += same ? ws[q] : 0;
-                  if (q < j && same) {
-                    first = false;
-                  }
-                }
-                if (first && rating > 0) {
-                  const Cand x{rating, 0, tie_hash(a.base_tie, u, keys[j]), keys[j]};
-                  if (cand_better<0>(x, top)) {
-                    top = x;
-                  }
-                  if (store_fav) {
-                    const Cand y{rating, 0, tie_hash(a.base_fav, u, keys[j]), keys[j]};
-                    if (cand_better<0>(y, fav)) {
-                      fav = y;
+              for (int j = 0; j < N; ++j) {
+                run += EW ? ws[j] : 1;
+                const bool last = (j == N - 1) || (keys[j + 1 < N ? j + 1 : j] != keys[j]);
+                if (last) {
+                  const int32_t rating = run;
+                  run = 0;
+                  if (keys[j] != kEmpty && rating > 0) {
+                    if (rating >= top.gain) {
+                      const Cand x{rating, 0, tie_hash(a.base_tie, u, keys[j]), keys[j]};
+                      if (cand_better<0>(x, top)) {
+                        top = x;
+                      }
+                    }
+                    if (store_fav && rating >= fav.gain) {
+                      const Cand y{rating, 0, tie_hash(a.base_fav, u, keys[j]), keys[j]};
+                      if (cand_better<0>(y, fav)) {
+                        fav = y;
+                      }
                     }
                   }
                 }
               }
-            }
-            bool top_ok = true;
-            if (top.gain > 0) {
-              top_ok = (a.weight[top.key] + uw <= a.max_cluster_weight) || (top.key == own);
-              if (a.communities != nullptr) {
-                top_ok = top_ok && (a.communities[top.key] == a.communities[own]);
-              }
-            }
-            if (top_ok) {
-              best = top;
-              lazy_done = true;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < D; ++j) {
-            if (!lazy_done && !skip && keys[j] != kEmpty) {
-              bool rep = true;
-              int32_t rating = 0;
-#pragma unroll
-              for (int q = 0; q < D; ++q) {
-                const bool same = keys[q] == keys[j];
-                rating += same ? ws[q] : 0;
-                if (q < j && same) {
-                  rep = false;
+              bool top_ok = true;
+              if (top.gain > 0) {
+                top_ok = (a.weight[top.key] + uw <= a.max_cluster_weight) || (top.key == own);
+                if (a.communities != nullptr) {
+                  top_ok = top_ok && (a.communities[top.key] == a.communities[own]);
                 }
               }
-              if (rep) {
-                Cand f;
-                const Cand c = eval_candidate<MODE>(a, u, own, uw, own_w, keys[j], rating, store_fav, f);
-                if (cand_better<MODE>(c, best)) {
-                  best = c;
-                }
-                if (MODE == 0 && cand_better<0>(f, fav)) {
-                  fav = f; // same value the lazy pass found
+              if (top_ok) {
+                best = top;
+                lazy_done = true;
+              }
+            }
+            if (!lazy_done) {
+              int32_t run = 0;
+#pragma unroll
+              for (int j = 0; j < N; ++j) {
+                run += EW ? ws[j] : 1;
+                const bool last = (j == N - 1) || (keys[j + 1 < N ? j + 1 : j] != keys[j]);
+                if (last) {
+                  const int32_t rating = run;
+                  run = 0;
+                  if (keys[j] != kEmpty) {
+                    Cand f;
+                    const Cand c = eval_candidate<MODE>(a, u, own, uw, own_w, keys[j], rating, MODE == 0 ? false : store_fav, f);
+                    if (cand_better<MODE>(c, best)) {
+                      best = c;
+                    }
+                  }
                 }
               }
             }

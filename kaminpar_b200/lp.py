@@ -29,6 +29,7 @@ from .graph import CSRGraph
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libkaminpar_b200.so")
 _lib = None
+ABI_VERSION = 3  # include/kaminpar_b200_lp.h: KMP_LP_ABI_VERSION
 
 UINT32_MAX = 0xFFFFFFFF
 
@@ -66,10 +67,10 @@ class KmpStats(C.Structure):
         ("sweep_ms", C.c_float),
         ("sweep_launches", C.c_uint64),
         ("kernel_launches", C.c_uint64),
-        ("group_edges", C.c_uint64 * 8),
-        ("group_nodes", C.c_uint64 * 8),
-        ("group_launches", C.c_uint64 * 8),
-        ("group_sweep_ms", C.c_float * 12),
+        ("group_edges", C.c_uint64 * 12),
+        ("group_nodes", C.c_uint64 * 12),
+        ("group_launches", C.c_uint64 * 12),
+        ("group_sweep_ms", C.c_float * 16),
         ("pull_rounds", C.c_uint32),
         ("push_rounds", C.c_uint32),
     ]
@@ -94,6 +95,8 @@ def load_library():
         lib = C.CDLL(_LIB_PATH)
         lib.kmp_last_error.restype = C.c_char_p
         lib.kmp_lp_labels_device.restype = C.c_void_p
+        if lib.kmp_lp_abi_version() != ABI_VERSION:  # the ctypes structs below mirror exactly this header version
+            raise RuntimeError(f"{_LIB_PATH}: ABI version {lib.kmp_lp_abi_version()} != {ABI_VERSION}; rebuild the library")
         _lib = lib
     return _lib
 

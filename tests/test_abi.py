@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 35 and "kmp_contract_clustering" in syms
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
-    assert lib.kmp_lp_abi_version() == 2
+    assert lib.kmp_lp_abi_version() == 3
 
 
 def test_config_struct_layout_matches_header():
