@@ -59,7 +59,8 @@ constexpr int kCtrNodes = 16, kCtrScratch = 40, kCtrSize = 48;
 constexpr uint32_t kHubMinDegree = 8192;       // graphs with edge weights (32-bit ratings in the team tables)
 constexpr uint32_t kHubMinDegreeUnit = 16384;  // unit edge weights: 16-bit ratings, twice the slots
 constexpr int kSMs = 148;
-constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512)
+constexpr uint32_t kMaxHubWaves = 448; // work-queue cursors ctr32[64 .. 512), overflow counters ctr32[512 .. 960)
+constexpr uint32_t kCtr32Size = 1024;
 constexpr int kTagCommit = 12, kTagApply = 13, kTagPush = 14, kTagMisc = 15; // timing slots besides the tiers
 
 // kernel tier of a vertex of degree d >= 1
@@ -181,8 +182,11 @@ struct kmp_lp_handle {
   uint64_t hub_wave_slots = 1ull << 28; // 2 GiB of packed entries (KMP_HUB_WAVE_SLOTS overrides, for experiments)
   DevBuf<Cand> t4_part_best, t4_part_fav;
   uint64_t t4_max_slots = 0;
-  uint32_t hub_cap_pct = 300; // tier-4 table slots per 100 labels (KMP_HUB_CAP_PCT overrides, for experiments)
-  DevBuf<unsigned long long> hub_tab; // packed (key << 32 | rating) entries, kEmpty64 when unused
+  uint64_t t4_max_wave_edges = 0; // largest adjacency volume of a wave = capacity of the overflow list
+  uint32_t hub_bucket_cap = kBucketCap, hub_sel_limit = 0; // KMP_HUB_BUCKET_CAP / KMP_HUB_SEL_LIMIT (tests: force the overflow paths)
+  DevBuf<unsigned long long> hub_tab; // bucket regions: kBucketCap packed (key << 32 | rating) entries each
+  DevBuf<uint32_t> hub_cursor;        // per bucket: entries appended in the running sub-round
+  DevBuf<HubOverflow> hub_ovf;
   uint32_t mover_cap = 0;
   uint32_t cur_subround = 0; // hashed class of the running sub-round
   uint32_t cur_sg = 0;       // running sub-round index in [0, 4 * S): queue cursor and stamp code
@@ -330,12 +334,6 @@ template <bool P64> __global__ void k_age_stamps(uint32_t n, void *labg, uint32_
     if (st != 0 && ((st - 1u) >> kStampBits) == parity) {
       g[u] = LabG<P64>::pack(LabG<P64>::label(w), 0);
     }
-  }
-}
-__global__ void k_fill_u64(uint64_t n, unsigned long long *p, unsigned long long v) {
-  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-    p[i] = v;
   }
 }
 __global__ void k_fill_u8(uint32_t n, uint8_t *p, uint8_t v) {
@@ -624,6 +622,7 @@ template <int MODE, bool EW, bool P64> void configure_team_kernels() {
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 32, 512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 8 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 128, 2048, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 4 * 8);
   cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 512, 8192, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+  cudaFuncSetAttribute(sweep_hub_scatter<MODE, EW, P64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHubScatterSmem);
   if constexpr (EW) {
     cudaFuncSetAttribute(sweep_team<MODE, EW, P64, 1024, 16384, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
   } else {
@@ -674,12 +673,16 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
     const uint32_t first = h->list_off[kHubTier * S + s_idx] - h->list_off[kHubTier * S];
     hb.table_off = h->t4_table_off.p + first;
     hb.g_tab = h->hub_tab.p;
-    hb.cap_pct = h->hub_cap_pct;
+    hb.cursor = h->hub_cursor.p;
+    hb.ovf = h->hub_ovf.p;
+    hb.ovf_cap = static_cast<uint32_t>(std::min<uint64_t>(h->t4_max_wave_edges, 0xFFFFFFFFull));
+    hb.bucket_cap = h->hub_bucket_cap;
+    hb.sel_limit = h->hub_sel_limit;
     hb.rank = h->rank;
     hb.world = h->world;
     hb.sel_begin = h->t4_sel_begin.p + first;
     hb.hit = h->t4_hit.p + first;
-    // one aggregate + partial-select pair per wave; all waves share the table memory (kept clean by the select)
+    // one scatter + select pair per wave; all waves share the bucket memory (cursors reset by the select)
     for (uint32_t w = h->t4_wave_off[s_idx]; w < h->t4_wave_off[s_idx + 1]; ++w) {
       const kmp_lp_handle::HubWave &wv = h->t4_waves[w];
       hb.item_entry = h->t4_item_entry.p + wv.item_lo;
@@ -689,13 +692,14 @@ template <int MODE, bool EW, bool P64> cudaError_t launch_sweep_t(kmp_lp_handle 
       hb.item_deg = h->t4_item_deg.p + wv.item_lo;
       hb.num_items = wv.item_hi - wv.item_lo;
       hb.queue = h->ctr32.p + 64 + w; // zeroed with the other per-round counters
-      sweep_hub_aggregate<MODE, EW, P64><<<std::min<uint32_t>(hb.num_items, kSMs * 5), kHubThreads, 0, h->sweep_stream>>>(a, hb, h->m);
+      hb.ovf_count = h->ctr32.p + 512 + w;
+      sweep_hub_scatter<MODE, EW, P64><<<std::min<uint32_t>(hb.num_items, kSMs * 4), kHubThreads, kHubScatterSmem, h->sweep_stream>>>(a, hb, h->m);
       hb.sel_entry = h->t4_sel_entry.p + wv.sel_lo;
       hb.sel_piece = h->t4_sel_piece.p + wv.sel_lo;
       hb.num_sel_items = wv.sel_hi - wv.sel_lo;
       hb.part_best = h->t4_part_best.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
       hb.part_fav = h->t4_part_fav.p + (wv.sel_lo - h->t4_sel_off[s_idx]);
-      sweep_hub_partial<MODE><<<std::min<uint32_t>(hb.num_sel_items, kSMs * 16), kChunkThreads, 0, h->sweep_stream>>>(a, hb);
+      sweep_hub_select<MODE><<<std::min<uint32_t>((hb.num_sel_items + kSelWarps - 1) / kSelWarps, kSMs * 6), kSelWarps * 32, 0, h->sweep_stream>>>(a, hb);
       h->kernel_launches += 2;
     }
     hb.part_best = h->t4_part_best.p;
@@ -795,8 +799,8 @@ int ensure_lists(kmp_lp_handle *h) {
   KMP_CUDA(h->sort_keys_out.ensure(n));
   KMP_CUDA(h->sort_vals_in.ensure(n));
   KMP_CUDA(h->order.ensure(n));
-  KMP_CUDA(h->ctr32.ensure(512));
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
+  KMP_CUDA(h->ctr32.ensure(kCtr32Size));
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, kCtr32Size * sizeof(uint32_t), h->stream));
   tc.lap("lists: buffers");
   const uint32_t base_sr = sync_base(h->cfg.seed, 0, 0, SALT_SUBROUND);
   // Sub-rounds per degree group: S for a group holding >= 1/16 of the visited vertices, S/4 otherwise
@@ -812,7 +816,7 @@ int ensure_lists(kmp_lp_handle *h) {
     for (int q = 0; q < 4; ++q) {
       gs.s[q] = (16ull * cnt[q] >= visited) ? S : std::max<uint32_t>(1, S / 4);
     }
-    KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream));
+    KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, kCtr32Size * sizeof(uint32_t), h->stream));
   }
   tc.lap("lists: group counts (sync)");
   k_list_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->xadj, S, gs, h->cfg.sync_granule_log2, base_sr,
@@ -859,6 +863,7 @@ int ensure_lists(kmp_lp_handle *h) {
     h->t4_wave_off.assign(S + 1, 0);
     h->t4_waves.clear();
     h->t4_max_slots = 0;
+    h->t4_max_wave_edges = 0;
     if (t4_cnt > 0) {
       DevBuf<uint32_t> &d_deg = h->t4_tmp_deg, &d_beg = h->t4_tmp_beg, &d_ids = h->t4_tmp_ids; // grow-only
       KMP_CUDA(d_deg.ensure(t4_cnt));
@@ -880,13 +885,13 @@ int ensure_lists(kmp_lp_handle *h) {
       {
         uint64_t total = 0;
         for (uint32_t i = 0; i < t4_cnt; ++i) {
-          total += hub_cap(deg[i], 0xFFFFFFFFu, h->hub_cap_pct);
+          total += static_cast<uint64_t>(hub_buckets(deg[i])) * kBucketCap;
         }
         wave_slots = std::max<uint64_t>(wave_slots, total / (kMaxHubWaves / 2 - S) + 1);
       }
       for (uint32_t sr = 0; sr < S; ++sr) {
         const uint32_t lo = h->list_off[kHubTier * S + sr] - t4_begin, hi = h->list_off[kHubTier * S + sr + 1] - t4_begin;
-        uint64_t slots = 0;
+        uint64_t slots = 0, wave_edges = 0;
         kmp_lp_handle::HubWave wave{static_cast<uint32_t>(ient.size()), 0, static_cast<uint32_t>(sent.size()), 0};
         auto close_wave = [&]() {
           wave.item_hi = static_cast<uint32_t>(ient.size());
@@ -897,18 +902,22 @@ int ensure_lists(kmp_lp_handle *h) {
           wave.item_lo = wave.item_hi;
           wave.sel_lo = wave.sel_hi;
           h->t4_max_slots = std::max(h->t4_max_slots, slots);
+          h->t4_max_wave_edges = std::max(h->t4_max_wave_edges, wave_edges);
           slots = 0;
+          wave_edges = 0;
         };
         for (uint32_t i = lo; i < hi; ++i) {
-          const uint64_t cap = hub_cap(deg[i], 0xFFFFFFFFu, h->hub_cap_pct);
-          if (static_cast<uint64_t>(deg[i]) * h->hub_cap_pct / 100 + 1 > 0xFFFFFFFFull) {
-            return fail(KMP_ERR_UNSUPPORTED, "high-degree table of one vertex exceeds 2^32 slots");
-          }
+          const uint32_t buckets = hub_buckets(deg[i]);
+          const uint64_t cap = static_cast<uint64_t>(buckets) * kBucketCap;
           if (slots > 0 && slots + cap > wave_slots) {
             close_wave();
           }
-          toff[i] = static_cast<uint32_t>(slots);
+          if ((slots + cap) / kBucketCap > 0xFFFFFFFFull) {
+            return fail(KMP_ERR_UNSUPPORTED, "high-degree buckets of one wave exceed 2^32");
+          }
+          toff[i] = static_cast<uint32_t>(slots / kBucketCap); // first bucket of the entry, wave-relative
           slots += cap;
+          wave_edges += deg[i];
           const uint32_t chunks = (deg[i] + kChunkEdges - 1) / kChunkEdges;
           for (uint32_t c = 0; c < chunks; ++c) {
             ient.push_back(i - lo);
@@ -918,8 +927,7 @@ int ensure_lists(kmp_lp_handle *h) {
             ideg.push_back(deg[i]);
           }
           sbeg[i] = static_cast<uint32_t>(sent.size() - h->t4_sel_off[sr]);
-          const uint32_t pieces = static_cast<uint32_t>((cap + kSelPieceSlots - 1) / kSelPieceSlots);
-          for (uint32_t c = 0; c < pieces; ++c) {
+          for (uint32_t c = 0; c < buckets; ++c) { // one selection item per bucket
             sent.push_back(i - lo);
             spiece.push_back(c);
           }
@@ -978,7 +986,7 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
   KMP_CUDA(h->mv_u.ensure(cap));
   KMP_CUDA(h->mv_t.ensure(cap));
   KMP_CUDA(h->acc.ensure(cap));
-  KMP_CUDA(h->ctr32.ensure(512));
+  KMP_CUDA(h->ctr32.ensure(kCtr32Size));
   KMP_CUDA(h->ctr64.ensure(kCtrSize));
   KMP_CUDA(h->active.ensure(h->n));
   if (mode == 0) {
@@ -1004,10 +1012,11 @@ int ensure_scratch(kmp_lp_handle *h, int mode, uint32_t num_labels) {
     KMP_CUDA(cudaMemsetAsync(h->hist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
     KMP_CUDA(cudaMemsetAsync(h->ohist.p, 0, kk * kLadderLevels * sizeof(int32_t), h->stream));
   }
-  // global table regions of tier 4 (kept clean by sweep_hub_partial)
-  if (h->t4_max_slots > 0 && h->hub_tab.cap < h->t4_max_slots) {
-    KMP_CUDA(h->hub_tab.ensure(h->t4_max_slots));
-    k_fill_u64<<<grid_for(h->t4_max_slots, 256), 256, 0, h->stream>>>(h->t4_max_slots, h->hub_tab.p, kEmpty64);
+  // bucket regions, cursors and overflow list of the hub tier
+  if (h->t4_max_slots > 0) {
+    KMP_CUDA(h->hub_tab.ensure(h->t4_max_slots)); // no initialisation: the cursors say how much of a region is valid
+    KMP_CUDA(h->hub_cursor.ensure(h->t4_max_slots / kBucketCap));
+    KMP_CUDA(h->hub_ovf.ensure(std::max<uint64_t>(h->t4_max_wave_edges, 1)));
     KMP_CUDA(cudaGetLastError());
   }
   (void)num_labels;
@@ -1352,8 +1361,11 @@ void choose_activation(kmp_lp_handle *h, uint32_t iter) {
 }
 
 int begin_iteration(kmp_lp_handle *h, uint32_t iter) {
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, kCtr32Size * sizeof(uint32_t), h->stream)); // proposal counters, moved, hub queues
   KMP_CUDA(cudaMemsetAsync(h->queue.p, 0, h->queue.cap * sizeof(uint32_t), h->stream));
+  if (h->hub_cursor.p != nullptr) { // normally already zero (sweep_hub_select resets what it reads)
+    KMP_CUDA(cudaMemsetAsync(h->hub_cursor.p, 0, h->hub_cursor.cap * sizeof(uint32_t), h->stream));
+  }
   if (h->world > 1 && h->comm != nullptr && h->dist_send.p != nullptr) {
     KMP_CUDA(cudaMemsetAsync(h->dist_send.p, 0, sizeof(uint32_t), h->stream)); // proposal counter of the send buffer
   }
@@ -1944,8 +1956,11 @@ int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out) {
     return fail(KMP_ERR_ALLOC, "out of host memory");
   }
   h->cfg = *cfg;
-  if (const char *e = std::getenv("KMP_HUB_CAP_PCT")) { // experiment knobs; results do not depend on them
-    h->hub_cap_pct = std::max(110, std::atoi(e));
+  if (const char *e = std::getenv("KMP_HUB_BUCKET_CAP")) { // experiment / test knobs; results do not depend on them
+    h->hub_bucket_cap = static_cast<uint32_t>(std::min<long>(kBucketCap, std::max(1, std::atoi(e))));
+  }
+  if (const char *e = std::getenv("KMP_HUB_SEL_LIMIT")) {
+    h->hub_sel_limit = static_cast<uint32_t>(std::max(0, std::atoi(e)));
   }
   if (const char *e = std::getenv("KMP_THREAD_MAX_DEG")) {
     h->thread_max_deg = static_cast<uint32_t>(std::max(16, std::atoi(e)));
@@ -2398,8 +2413,11 @@ int kmp_lp_select_all(kmp_lp_handle *h, int mode, const uint32_t *labels, const 
   RunCtx ctx{mode, num_labels, max_cluster_weight, mode == 1 && min_weights != nullptr, false};
   SweepArgs sa = make_sweep_args(h, ctx);
   sa.active = nullptr;
-  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, 512 * sizeof(uint32_t), h->stream)); // hub work-queue cursors
+  KMP_CUDA(cudaMemsetAsync(h->ctr32.p, 0, kCtr32Size * sizeof(uint32_t), h->stream)); // hub work-queue cursors
   KMP_CUDA(cudaMemsetAsync(h->queue.p, 0, h->queue.cap * sizeof(uint32_t), h->stream));
+  if (h->hub_cursor.p != nullptr) {
+    KMP_CUDA(cudaMemsetAsync(h->hub_cursor.p, 0, h->hub_cursor.cap * sizeof(uint32_t), h->stream));
+  }
   sa.sel_target = d_target.p;
   sa.sel_favored = mode == 0 ? d_fav.p : nullptr;
   sa.base_tie = sync_base(h->cfg.seed, call_index, iteration, SALT_TIE);
@@ -2452,6 +2470,8 @@ int kmp_lp_free_scratch(kmp_lp_handle *h) {
   h->ctr32.release();
   h->ctr64.release();
   h->hub_tab.release();
+  h->hub_cursor.release();
+  h->hub_ovf.release();
   h->labg.release();
   h->sort_keys_in.release();
   h->sort_keys_out.release();

@@ -309,53 +309,6 @@ __device__ __forceinline__ void table_add(uint32_t *keys, int32_t *vals, uint32_
   }
 }
 
-// Global hub tables hold packed 64-bit entries (key << 32 | rating); empty = 0xFFFFFFFF00000000.
-// The first insertion of a key is ONE atomicCAS that also deposits the rating; later partial
-// ratings are one 64-bit atomicAdd on the same entry (ratings are non-negative int32 sums).
-constexpr unsigned long long kEmpty64 = 0xFFFFFFFF00000000ull;
-
-// B independent inserts: the first probe of all B keys is a plain L2 load (ld.cg), issued for the whole
-// batch before any result is consumed. A key that is already present then costs one fire-and-forget
-// RED; an empty slot is claimed with one CAS that also deposits the rating.
-template <int B>
-__device__ __forceinline__ void table64_add_batch(unsigned long long *tab, uint32_t cap, bool direct,
-                                                  const uint32_t (&k)[B], const int32_t (&w)[B]) {
-  uint32_t slot[B];
-  unsigned long long prev[B];
-#pragma unroll
-  for (int j = 0; j < B; ++j) {
-    slot[j] = direct ? k[j] : __umulhi(lowbias32(k[j]), cap); // cap need not be a power of two
-    prev[j] = kEmpty64;
-    if (k[j] != kEmpty) {
-      prev[j] = __ldcg(&tab[slot[j]]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < B; ++j) {
-    if (k[j] == kEmpty) {
-      continue;
-    }
-    const unsigned long long mine = (static_cast<unsigned long long>(k[j]) << 32) | static_cast<uint32_t>(w[j]);
-    uint32_t sl = slot[j];
-    unsigned long long pv = prev[j];
-    while (true) {
-      if (static_cast<uint32_t>(pv >> 32) == k[j]) {
-        atomicAdd(&tab[sl], static_cast<unsigned long long>(static_cast<uint32_t>(w[j])));
-        break;
-      }
-      if (pv == kEmpty64) { // the slot looked empty: claim it
-        pv = atomicCAS(&tab[sl], kEmpty64, mine);
-        if (pv == kEmpty64) {
-          break;
-        }
-        continue; // somebody else claimed it first: re-examine the same slot
-      }
-      sl = sl + 1 == cap ? 0 : sl + 1;
-      pv = __ldcg(&tab[sl]);
-    }
-  }
-}
-
 // ================================================================================================
 // tiers 2..5: a TEAM of T threads (one warp, 128, 512 or 1024 threads) per vertex, rating map = an
 // open-addressing table in shared memory sized for the tier's largest degree (load <= 0.5).
@@ -670,24 +623,55 @@ __global__ void __launch_bounds__(T *TEAMS) sweep_team(const SweepArgs a) {
 }
 
 // ================================================================================================
-// tier 7 (deg >= 8192 / 16384): edge-parallel. Phase 1: one CTA per 4096-edge chunk aggregates ratings in a
-// shared-memory hash map and merges the distinct keys into the vertex's global table region.
-// Phase 2: one CTA per vertex scans its region, selects, and clears it.
+// tier 7 (deg >= 8192 / 16384): edge-parallel, label-partitioned two-pass aggregation. No random access ever
+// touches a table outside shared memory, and after the chunk is staged every warp works on its own:
+//   scatter : a CTA takes 2048-edge chunks of hub adjacencies from a work queue. The producer warp stages each
+//             chunk with one 1-D bulk TMA copy; each of the 8 consumer warps gathers the labels of its 256-edge
+//             slice, aggregates them in its private 512-slot shared-memory hash map (slice-local ratings: a label
+//             that dominates the neighbourhood costs one entry per slice, not one per edge) and appends every
+//             distinct (label, rating) to the BUCKET lowbias32(label) & (P-1) of the vertex -- P = hub_buckets(deg)
+//             buckets of kBucketCap packed 8-byte entries each, filled through one atomic cursor per bucket
+//             (streaming writes). An append beyond a bucket's capacity (possible only with skewed label hashes: the
+//             expected fill is <= 256 of 512) goes to a shared overflow list, so nothing is ever dropped.
+//   select  : one WARP per (vertex, bucket) streams the bucket's entries into its private 1024-slot hash map,
+//             ranks the distinct labels and writes the bucket's best / favored candidate. Labels of different
+//             buckets are disjoint, so the vertex's decision is the arg-max over its buckets (final). A bucket
+//             that also has overflow entries may exceed the map: it is then processed in K = 2, 4, ... passes over
+//             disjoint hash classes (lowbias32 is a bijection, so the classes eventually separate all labels).
+//   final   : one warp per vertex reduces its buckets' candidates and proposes / stores the favored cluster.
 // ================================================================================================
 constexpr int kChunkEdges = 2048;
-constexpr int kChunkTableSlots = 4096; // 32 KiB dynamic shared memory: 7 CTAs per SM
+constexpr int kSliceEdges = 256;        // edges per consumer warp and chunk
+constexpr int kSliceTableSlots = 512;   // warp-private map of the scatter pass: <= 256 distinct labels, load <= 0.5
 constexpr int kChunkThreads = 256;
+constexpr uint32_t kBucketCap = 512;       // entries per bucket region
+constexpr uint32_t kBucketTargetFill = 256;
+constexpr uint32_t kSelTableSlots = 1024;  // warp-private map of the select pass
+constexpr int kSelWarps = 4;               // warps (= buckets in flight) per select CTA: 32 KiB of shared memory
+
+struct HubOverflow { // an entry that did not fit its bucket region
+  uint32_t bucket;   // wave-relative bucket index
+  uint32_t key;
+  int32_t rating;
+  uint32_t pad;
+};
 
 struct HubArgs {
-  const uint32_t *__restrict__ item_entry; // index into the tier-4 list of this sub-round
+  const uint32_t *__restrict__ item_entry; // index into the hub list of this sub-round
   const uint32_t *__restrict__ item_chunk;
   const uint32_t *__restrict__ item_u;   // static per item: vertex id, xadj[u], degree
   const uint32_t *__restrict__ item_beg;
   const uint32_t *__restrict__ item_deg;
   uint32_t num_items;
-  const uint32_t *__restrict__ table_off;  // per list entry: first slot of its region
-  unsigned long long *__restrict__ g_tab; // packed entries
-  // phase 2 (partial selection over 8192-slot pieces of the region)
+  const uint32_t *__restrict__ table_off;  // per list entry: its first bucket (wave-relative)
+  unsigned long long *__restrict__ g_tab;  // bucket regions: kBucketCap packed (key << 32 | rating) entries each
+  uint32_t *__restrict__ cursor;           // per bucket: entries appended (zero between sub-rounds: select resets it)
+  HubOverflow *__restrict__ ovf;           // overflow list of the running wave
+  uint32_t *__restrict__ ovf_count;        // its length (per wave; zeroed with the per-round counters)
+  uint32_t ovf_cap;
+  uint32_t bucket_cap;                     // entries a region takes (kBucketCap; smaller only in tests: KMP_HUB_BUCKET_CAP)
+  uint32_t sel_limit;                      // 0, or a smaller claim limit of the select map (tests: KMP_HUB_SEL_LIMIT)
+  // select: one item per (list entry, bucket)
   const uint32_t *__restrict__ sel_entry;
   const uint32_t *__restrict__ sel_piece;
   uint32_t num_sel_items;
@@ -695,18 +679,18 @@ struct HubArgs {
   Cand *__restrict__ part_best;           // per selection item
   Cand *__restrict__ part_fav;
   uint32_t rank, world;                   // hub entry i is owned by rank i % world
-  uint32_t cap_pct;                       // table slots per 100 distinct labels (hub_cap)
   uint32_t *__restrict__ queue;           // work-queue cursor of this launch (zeroed per LP round)
   uint32_t *__restrict__ hit;             // per list entry: a neighbour moved since the last visit (pull); reset by final
 };
-constexpr uint32_t kSelPieceSlots = 8192;
 
-// slots of a hub's table region: pct/100 x the number of labels it can meet (not a power of two: the
-// region is written and scanned in full every sub-round, so its size is DRAM traffic)
-__host__ __device__ __forceinline__ uint32_t hub_cap(uint32_t full_degree, uint32_t num_labels, uint32_t pct) {
-  const uint32_t distinct = full_degree < num_labels ? full_degree : num_labels;
-  const unsigned long long cap = static_cast<unsigned long long>(distinct) * pct / 100 + 1;
-  return cap < 32 ? 32u : static_cast<uint32_t>(cap);
+// buckets of a hub: a power of two with <= kBucketTargetFill expected distinct labels per bucket
+__host__ __device__ __forceinline__ uint32_t hub_buckets(uint32_t full_degree) {
+  const uint32_t need = (full_degree + kBucketTargetFill - 1) / kBucketTargetFill;
+  uint32_t p = 1;
+  while (p < need) {
+    p <<= 1;
+  }
+  return p;
 }
 
 // ---- 1-D bulk TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------
@@ -754,20 +738,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kHubStages = 3;
+constexpr int kHubStages = 2;
 constexpr int kHubConsumerWarps = kChunkThreads / 32;          // 8 consumer warps
 constexpr int kHubThreads = kChunkThreads + 32;                // + 1 producer warp
+constexpr int kHubScatterSmem = kHubConsumerWarps * kSliceTableSlots * 8; // dynamic: 8 warp maps (keys + ratings)
 
 template <int MODE, bool EW, bool P64>
-__global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
-  // Phase 1 of tier 4, warp-specialised producer / consumer pipeline (3 stages):
-  //   producer warp : evaluates the next work item (2048-edge chunk of a hub's adjacency), publishes
-  //                   its descriptor and stages the chunk into shared memory with ONE bulk TMA copy
-  //                   (cp.async.bulk, completion on the stage's `full` mbarrier);
-  //   consumer warps: wait on `full`, gather the neighbour labels (4 independent gathers per lane),
-  //                   de-duplicate the 32 labels of a warp-batch with match.any and merge each
-  //                   group's rating into the vertex's global table region with one 64-bit atomic;
-  //                   then release the stage through the `empty` mbarrier.
+__global__ void __launch_bounds__(kHubThreads, 4) sweep_hub_scatter(const SweepArgs a, const HubArgs hb, uint32_t m_total) {
+  // warp-specialised producer / consumer pipeline:
+  //   producer warp : claims the next work item (2048-edge chunk of a hub's adjacency), publishes its descriptor
+  //                   and stages the chunk with ONE bulk TMA copy (cp.async.bulk, completion on the stage's `full`
+  //                   mbarrier);
+  //   consumer warps: wait on `full`; each warp gathers the neighbour labels of its 256-edge slice (4 independent
+  //                   gathers per lane) into its private map, releases the stage (`empty` mbarrier), then appends
+  //                   the map's entries to the vertex's buckets and clears it. No barrier between warps.
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int kAllSlots = kHubConsumerWarps * kSliceTableSlots;
+  uint32_t *all_keys = reinterpret_cast<uint32_t *>(smem_raw);
+  int32_t *all_vals = reinterpret_cast<int32_t *>(smem_raw + sizeof(uint32_t) * kAllSlots);
   __shared__ __align__(16) uint32_t s_adj[kHubStages][kChunkEdges + 8];
   __shared__ __align__(8) uint64_t s_full[kHubStages];
   __shared__ __align__(8) uint64_t s_empty[kHubStages];
@@ -780,6 +768,10 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
       mbar_init(&s_empty[s], kHubConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int s = threadIdx.x; s < kAllSlots; s += kHubThreads) {
+    all_keys[s] = kEmpty;
+    all_vals[s] = 0;
   }
   __syncthreads();
 
@@ -850,6 +842,8 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
   }
 
   // --------------------------------- consumer warps ----------------------------------------------
+  uint32_t *keys = all_keys + wib * kSliceTableSlots;
+  int32_t *vals = all_vals + wib * kSliceTableSlots;
   for (uint32_t k = 0;; ++k) {
     const int stage = static_cast<int>(k % kHubStages);
     const uint32_t round = k / kHubStages;
@@ -858,13 +852,14 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
     if (d.valid == 2) {
       break; // queue exhausted
     }
-    if (d.valid) {
-      const uint32_t gcap = hub_cap(d.full_deg, a.num_labels, hb.cap_pct);
-      const bool gdirect = a.num_labels <= gcap;
-      unsigned long long *gt = hb.g_tab + hb.table_off[d.entry];
+    const uint32_t wbeg = d.gbeg + wib * kSliceEdges;
+    const bool mine = d.valid && wbeg < d.gend;
+    if (mine) {
+      const uint32_t wend = wbeg + kSliceEdges < d.gend ? wbeg + kSliceEdges : d.gend;
       const uint32_t staged_end = d.a0 + d.staged;
       bool hit = false;
-      for (uint32_t e0 = d.gbeg + wib * 128; e0 < d.gend; e0 += kHubConsumerWarps * 128) {
+      // ---- gather + slice-local aggregation
+      for (uint32_t e0 = wbeg; e0 < wend; e0 += 128) {
         uint32_t k4[4];
         int32_t w4[4];
 #pragma unroll
@@ -872,7 +867,7 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
           const uint32_t e = e0 + j * 32 + lane;
           k4[j] = kEmpty;
           w4[j] = 0;
-          if (e < d.gend) {
+          if (e < wend) {
             const uint32_t v = e < staged_end ? s_adj[stage][e - d.a0] : a.adjncy[e];
             bool ok = true;
             if (MODE == 1 && a.communities != nullptr) {
@@ -888,117 +883,265 @@ __global__ void __launch_bounds__(kHubThreads, 5) sweep_hub_aggregate(const Swee
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const unsigned peers = __match_any_sync(kFull, k4[j]);
-          int32_t r;
-          if (EW) {
-            r = 0;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const int32_t wq = __shfl_sync(kFull, w4[j], q);
-              r += ((peers >> q) & 1u) ? wq : 0;
-            }
-          } else {
-            r = __popc(peers);
+          if (k4[j] != kEmpty) {
+            table_add(keys, vals, kSliceTableSlots - 1, false, k4[j], w4[j]);
           }
-          const bool leader = lane == __ffs(peers) - 1;
-          if (!leader) {
-            k4[j] = kEmpty;
-          }
-          w4[j] = r;
         }
-        table64_add_batch<4>(gt, gcap, gdirect, k4, w4);
       }
       if (a.pull && __any_sync(kFull, hit) && lane == 0) {
         atomicOr(&hb.hit[d.entry], 1u);
       }
     }
-    __syncwarp();
+    __syncwarp(); // the warp's map is complete, its reads of the staged adjacency are done
     if (lane == 0) {
-      mbar_arrive(&s_empty[stage]); // this warp is done with the stage
+      mbar_arrive(&s_empty[stage]);
     }
-  }
-}
-
-// Phase 2a: one CTA per 8192-slot piece of a hub's region: best candidates of the piece.
-template <int MODE> __global__ void __launch_bounds__(kChunkThreads) sweep_hub_partial(const SweepArgs a, const HubArgs hb) {
-  __shared__ Cand s_best[kChunkThreads / 32];
-  __shared__ Cand s_fav[kChunkThreads / 32];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int wib = tid >> 5;
-  for (uint32_t it = blockIdx.x; it < hb.num_sel_items; it += gridDim.x) {
-    const uint32_t entry = hb.sel_entry[it];
-    const uint32_t u = a.list[entry];
-    Cand c = cand_none(), f = cand_none();
-    // the region is scanned (and cleaned) whenever it was aggregated; activity is decided by sweep_hub_final
-    const bool act = (entry % hb.world == hb.rank) && (a.active == nullptr || a.pull || a.active[u] != 0);
-    if (act) {
-      const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
-      const uint32_t own = a.label[u];
-      const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
-      const int32_t own_w = a.weight[own];
-      const uint32_t gcap = hub_cap(full_deg, a.num_labels, hb.cap_pct);
-      const uint32_t lo = hb.sel_piece[it] * kSelPieceSlots;
-      const uint32_t hi = lo + kSelPieceSlots < gcap ? lo + kSelPieceSlots : gcap;
-      unsigned long long *gt = hb.g_tab + hb.table_off[entry];
-      const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
-      constexpr int B = 8; // slots per thread and batch: B independent loads in flight per stage
-      for (uint32_t s0 = lo; s0 < hi; s0 += kChunkThreads * B) {
-        uint32_t kk[B];
-        int32_t rr[B], ww[B];
+    if (mine) {
+      // ---- append the distinct (label, rating) pairs to the vertex's buckets, clear the map
+      const uint32_t pmask = hub_buckets(d.full_deg) - 1;
+      const uint32_t bucket0 = hb.table_off[d.entry];
+      constexpr int B = 4; // B independent cursor atomics in flight per lane
+      for (uint32_t s0 = lane; s0 < kSliceTableSlots; s0 += 32 * B) {
+        uint32_t kk[B], bb[B], pos[B];
+        int32_t rr[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          const uint32_t s = s0 + j * kChunkThreads + tid;
-          const unsigned long long e = s < hi ? __ldcg(gt + s) : kEmpty64;
-          kk[j] = static_cast<uint32_t>(e >> 32);
-          rr[j] = static_cast<int32_t>(static_cast<uint32_t>(e));
+          const uint32_t s = s0 + j * 32;
+          kk[j] = keys[s];
+          rr[j] = vals[s];
+          if (kk[j] != kEmpty) {
+            keys[s] = kEmpty;
+            vals[s] = 0;
+          }
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          ww[j] = kk[j] != kEmpty ? a.weight[kk[j]] : 0;
+          bb[j] = bucket0 + (lowbias32(kk[j]) & pmask);
+          pos[j] = kk[j] != kEmpty ? atomicAdd(&hb.cursor[bb[j]], 1u) : 0u;
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
           if (kk[j] != kEmpty) {
-            gt[s0 + j * kChunkThreads + tid] = kEmpty64;
-            Cand ff;
-            const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kk[j], rr[j], ww[j], store_fav, ff);
-            if (cand_better<MODE>(cc, c)) {
-              c = cc;
-            }
-            if (MODE == 0 && cand_better<0>(ff, f)) {
-              f = ff;
+            if (pos[j] < hb.bucket_cap) {
+              hb.g_tab[static_cast<size_t>(bb[j]) * kBucketCap + pos[j]] =
+                  (static_cast<unsigned long long>(kk[j]) << 32) | static_cast<uint32_t>(rr[j]);
+            } else {
+              const uint32_t o = atomicAdd(hb.ovf_count, 1u); // < ovf_cap: at most one entry per edge of the wave
+              if (o < hb.ovf_cap) {
+                hb.ovf[o] = HubOverflow{bb[j], kk[j], rr[j], 0u};
+              }
             }
           }
         }
       }
+      __syncwarp(); // map clean before the warp's next slice
     }
-    const Cand wb = warp_argmax<MODE>(kFull, c);
-    const Cand wf = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
-    if (lane == 0) {
-      s_best[wib] = wb;
-      s_fav[wib] = wf;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      Cand best = cand_none(), fav = cand_none();
-#pragma unroll
-      for (int q = 0; q < kChunkThreads / 32; ++q) {
-        if (cand_better<MODE>(s_best[q], best)) {
-          best = s_best[q];
-        }
-        if (MODE == 0 && cand_better<0>(s_fav[q], fav)) {
-          fav = s_fav[q];
-        }
-      }
-      hb.part_best[it] = best;
-      hb.part_fav[it] = fav;
-    }
-    __syncthreads();
   }
 }
 
-// Phase 2b: one warp per hub: reduce its partial results, then propose / store the favored cluster.
+// select: one warp per (hub, bucket): best candidates of the bucket's labels
+template <int MODE> __global__ void __launch_bounds__(kSelWarps * 32) sweep_hub_select(const SweepArgs a, const HubArgs hb) {
+  __shared__ uint32_t s_keys[kSelWarps][kSelTableSlots];
+  __shared__ int32_t s_vals[kSelWarps][kSelTableSlots];
+  __shared__ uint32_t s_claims_all[kSelWarps];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  uint32_t *keys = s_keys[wib];
+  int32_t *vals = s_vals[wib];
+  uint32_t *s_claims = &s_claims_all[wib];
+  for (uint32_t s = lane; s < kSelTableSlots; s += 32) {
+    keys[s] = kEmpty;
+    vals[s] = 0;
+  }
+  if (lane == 0) {
+    *s_claims = 0;
+  }
+  __syncwarp();
+  const uint32_t nwarps = gridDim.x * kSelWarps;
+  for (uint32_t it = blockIdx.x * kSelWarps + wib; it < hb.num_sel_items; it += nwarps) {
+    const uint32_t entry = hb.sel_entry[it];
+    const uint32_t u = a.list[entry];
+    Cand c = cand_none(), f = cand_none();
+    // a bucket is read (and its cursor reset) whenever the scatter pass may have filled it; activity is decided
+    // by sweep_hub_final
+    const bool act = (entry % hb.world == hb.rank) && (a.active == nullptr || a.pull || a.active[u] != 0);
+    const uint32_t b = hb.table_off[entry] + hb.sel_piece[it];
+    const uint32_t appended = act ? __ldcg(&hb.cursor[b]) : 0u;
+    if (appended != 0) {
+      const uint32_t full_deg = a.xadj[u + 1] - a.xadj[u];
+      const uint32_t pbits = 31 - __clz(static_cast<int>(hub_buckets(full_deg)));
+      const uint32_t own = a.label[u];
+      const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
+      const int32_t own_w = a.weight[own];
+      const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
+      const uint32_t n_reg = appended < hb.bucket_cap ? appended : hb.bucket_cap;
+      const uint32_t n_ovf = appended > hb.bucket_cap ? min(__ldcg(hb.ovf_count), hb.ovf_cap) : 0u;
+      // The map is sized for the entries at hand. A bucket without overflow entries holds <= kBucketCap =
+      // kSelTableSlots / 2 labels: it can never fill the map. K > 1 only when overflow entries push the distinct
+      // labels of this bucket beyond 5/8 of the map (checked after every batch of <= 128 inserts, so the map
+      // holds at most 640 + 128 < 1024 labels).
+      uint32_t tcap = pow2_ceil(2 * appended);
+      tcap = tcap < 64 ? 64u : tcap > kSelTableSlots ? kSelTableSlots : tcap;
+      const uint32_t tmask = tcap - 1;
+      const uint32_t full_limit = tcap / 2 + tcap / 8;
+      const uint32_t limit = (hb.sel_limit != 0 && hb.sel_limit < full_limit) ? hb.sel_limit : full_limit;
+      const unsigned long long *reg = hb.g_tab + static_cast<size_t>(b) * kBucketCap;
+      auto insert = [&](uint32_t key, int32_t r) {
+        uint32_t slot = lowbias32(key ^ 0x9E3779B9u) & tmask;
+        while (true) {
+          const uint32_t prev = atomicCAS(&keys[slot], kEmpty, key);
+          if (prev == kEmpty) {
+            atomicAdd(s_claims, 1u);
+          }
+          if (prev == kEmpty || prev == key) {
+            atomicAdd(&vals[slot], r);
+            return;
+          }
+          slot = (slot + 1) & tmask;
+        }
+      };
+      uint32_t K = 1;
+      while (true) {
+        c = cand_none();
+        f = cand_none();
+        bool overflowed = false;
+        for (uint32_t cls = 0; cls < K && !overflowed; ++cls) {
+          // ---- insert the entries of hash class `cls`
+          constexpr int B = 4;
+          for (uint32_t i0 = 0; i0 < n_reg && !overflowed; i0 += 32 * B) {
+            unsigned long long e[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              const uint32_t i = i0 + j * 32 + lane;
+              e[j] = i < n_reg ? __ldcs(reg + i) : ~0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              const uint32_t key = static_cast<uint32_t>(e[j] >> 32);
+              if (key != kEmpty && ((lowbias32(key) >> pbits) & (K - 1)) == cls) {
+                insert(key, static_cast<int32_t>(static_cast<uint32_t>(e[j])));
+              }
+            }
+            if (n_ovf != 0) { // with overflow entries (appended > bucket_cap, hence the full map): check the claims
+              __syncwarp();
+              overflowed = *s_claims > limit;
+              __syncwarp();
+            }
+          }
+          for (uint32_t i0 = 0; i0 < n_ovf && !overflowed; i0 += 32 * B) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              const uint32_t i = i0 + j * 32 + lane;
+              if (i < n_ovf) {
+                const HubOverflow o = hb.ovf[i];
+                if (o.bucket == b && ((lowbias32(o.key) >> pbits) & (K - 1)) == cls) {
+                  insert(o.key, o.rating);
+                }
+              }
+            }
+            __syncwarp();
+            overflowed = *s_claims > limit;
+            __syncwarp();
+          }
+          __syncwarp(); // the class is inserted (or abandoned)
+          // ---- evaluate + clear
+          bool lazy_done = false;
+          if (MODE == 0 && K == 1 && !overflowed) {
+            // Clusterer, single class: rank the labels WITHOUT their cluster weights (the team kernels do the
+            // same): if the bucket's top label is feasible it is the bucket's best; the favored label never needs
+            // weights. Only a full top label costs the second scan with one weight gather per label.
+            Cand ct = cand_none();
+            for (uint32_t s = lane; s < tcap; s += 32) {
+              const uint32_t kx = keys[s];
+              if (kx != kEmpty) {
+                const int32_t r = vals[s];
+                if (r >= ct.gain && r > 0) {
+                  const Cand x{r, 0, tie_hash(a.base_tie, u, kx), kx};
+                  if (cand_better<0>(x, ct)) {
+                    ct = x;
+                  }
+                }
+                if (store_fav && r >= f.gain && r > 0) {
+                  const Cand y{r, 0, tie_hash(a.base_fav, u, kx), kx};
+                  if (cand_better<0>(y, f)) {
+                    f = y;
+                  }
+                }
+              }
+            }
+            const Cand top = warp_argmax<0>(kFull, ct);
+            bool top_ok = true;
+            if (top.gain > 0) {
+              top_ok = (a.weight[top.key] + uw <= a.max_cluster_weight) || (top.key == own);
+              if (a.communities != nullptr) {
+                top_ok = top_ok && (a.communities[top.key] == a.communities[own]);
+              }
+            }
+            if (top_ok) {
+              c = top;
+              lazy_done = true;
+            }
+          }
+          const bool evaluate = !overflowed && !lazy_done;
+          for (uint32_t s0 = 0; s0 < tcap; s0 += 32 * B) {
+            uint32_t kk[B];
+            int32_t rr[B], ww[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              const uint32_t s = s0 + j * 32 + lane;
+              kk[j] = s < tcap ? keys[s] : kEmpty;
+              rr[j] = kk[j] != kEmpty ? vals[s] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              ww[j] = (kk[j] != kEmpty && evaluate) ? a.weight[kk[j]] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              if (kk[j] != kEmpty) {
+                const uint32_t s = s0 + j * 32 + lane;
+                keys[s] = kEmpty;
+                vals[s] = 0;
+                if (evaluate) {
+                  Cand ff;
+                  // (the favored candidate of the lazy pass is final: no second evaluation)
+                  const Cand cc = eval_candidate_w<MODE>(a, u, own, uw, own_w, kk[j], rr[j], ww[j],
+                                                         store_fav && !(MODE == 0 && K == 1), ff);
+                  if (cand_better<MODE>(cc, c)) {
+                    c = cc;
+                  }
+                  if (MODE == 0 && cand_better<0>(ff, f)) {
+                    f = ff;
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            *s_claims = 0;
+          }
+          __syncwarp();
+        }
+        if (!overflowed) {
+          break;
+        }
+        K <<= 1; // too many distinct labels for the map: split into more hash classes and start over
+      }
+      if (lane == 0) {
+        hb.cursor[b] = 0;
+      }
+    }
+    const Cand best = warp_argmax<MODE>(kFull, c);
+    const Cand fav = (MODE == 0) ? warp_argmax<0>(kFull, f) : cand_none();
+    if (lane == 0) {
+      hb.part_best[it] = best;
+      hb.part_fav[it] = fav;
+    }
+  }
+}
+
+// final: one warp per hub: reduce its buckets' candidates, then propose / store the favored cluster.
 template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const SweepArgs a, const HubArgs hb) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1034,8 +1177,7 @@ template <int MODE> __global__ void __launch_bounds__(256) sweep_hub_final(const
     const uint32_t own = a.label[u];
     const int32_t uw = a.vwgt != nullptr ? a.vwgt[u] : 1;
     const int32_t own_w = a.weight[own];
-    const uint32_t gcap = hub_cap(full_deg, a.num_labels, hb.cap_pct);
-    const uint32_t pieces = (gcap + kSelPieceSlots - 1) / kSelPieceSlots;
+    const uint32_t pieces = hub_buckets(full_deg);
     const uint32_t first = hb.sel_begin[i];
     const bool store_fav = (MODE == 0) && (uw == own_w) && (own_w <= a.max_cluster_weight / 2);
     Cand c = cand_none(), f = cand_none();

@@ -133,19 +133,31 @@ def test_t1_clustering_matches_oracle_sync(name, seed):
     assert np.array_equal(c2, expect2)
 
 
-@pytest.mark.parametrize("name", ["rmat15_sorted", "star_hub", "rmat14_unsorted_w"])
-@pytest.mark.parametrize("knobs", [("150", "6000"), ("300", "40000")])
-def test_t1_hub_table_layout_does_not_change_results(name, knobs, monkeypatch):
-    """The tier-4 table sizing and the wave budget are performance knobs (read once per handle): tight
-    tables and one-hub waves must give the oracle's clustering as well."""
-    monkeypatch.setenv("KMP_HUB_CAP_PCT", knobs[0])
-    monkeypatch.setenv("KMP_HUB_WAVE_SLOTS", knobs[1])
+@pytest.mark.parametrize("name", ["rmat15_sorted", "star_hub", "rmat14_unsorted_w", "rmat16_hubs", "rmat15_hubs_w"])
+@pytest.mark.parametrize("knobs", [("8", "200", "6000"), ("64", "0", "40000"), ("3072", "0", "20000")])
+def test_t1_hub_bucket_layout_does_not_change_results(name, knobs, monkeypatch):
+    """Bucket capacity, the claim limit of the select map and the wave budget of the hub tier are performance
+    knobs (read once per handle). Tiny buckets push almost every entry through the overflow list and a tiny claim
+    limit forces the multi-pass (hash class) selection; one-hub waves reuse the bucket memory: all of them must
+    give the oracle's clustering and refinement."""
+    monkeypatch.setenv("KMP_HUB_BUCKET_CAP", knobs[0])
+    monkeypatch.setenv("KMP_HUB_SEL_LIMIT", knobs[1])
+    monkeypatch.setenv("KMP_HUB_WAVE_SLOTS", knobs[2])
     g = get_graph(name)
     ctx, mcw = ctx_for(g, 8, seed=3)
     clusterer = lp.LPClustering(ctx.coarsening, ctx.engine)
     clusterer.set_max_cluster_weight(mcw)
     c = clusterer.compute_clustering(g)
     assert np.array_equal(c, B.oracle_lp_cluster(g, 3, mcw, schedule=B.SYNC))
+    k = 8
+    part = np.random.default_rng(5).integers(0, k, g.n).astype(np.uint32)
+    p_graph = lp.PartitionedGraph(g, k, part)
+    refiner = lp.LabelPropagationRefiner(ctx)
+    refiner.initialize(p_graph)
+    refiner.refine(p_graph, ctx.partition)
+    rp = B.oracle_params(B.default_refine_params(), commit_passes=4)
+    ep, ebw = B.oracle_lp_refine(g, 3, k, ctx.partition.max_block_weights(), part, schedule=B.SYNC, params=rp)
+    assert np.array_equal(p_graph.partition, ep) and np.array_equal(p_graph.block_weights(), ebw)
 
 
 @pytest.mark.parametrize("mode", ["push", "pull"])
