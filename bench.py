@@ -496,7 +496,7 @@ def main():
     peak, peak_src = peaks()
     names = ["sweep_thread<8>(deg<8)", "sweep_thread<16>(deg<=16)", "sweep_thread<32>(deg<32)",
              "sweep_team<32>(deg<256)", "sweep_team<128>(deg<1024)", "sweep_team<512>(deg<4096)", "sweep_team<1024>(deg<16384)",
-             "sweep_hub_aggregate+partial+final(deg>=16384)"]
+             "sweep_hub_scatter+select+final(deg>=16384)"]
     dom = int(np.argmax(g_ms))
     alg_bytes = 8 * g_edges[dom] + 16 * g_nodes[dom]
     achieved = alg_bytes / (g_ms[dom] * 1e-3) / 1e9 if g_ms[dom] > 0 else 0.0
