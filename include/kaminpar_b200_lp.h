@@ -103,7 +103,7 @@ typedef struct {
   uint64_t kernel_launches;  /* all kernel launches of the call */
   /* per kernel tier (8 in use: 0: deg<=7 sweep_thread<8>, 1: deg<=16 sweep_thread<16>, 2: deg<=31 sweep_thread<32>,
    * 3: deg<256 sweep_team<32>, 4: deg<1024 sweep_team<128>, 5: deg<4096 sweep_team<512>, 6: deg<8192 / 16384
-   * sweep_team<1024>, 7: above: sweep_hub_aggregate+partial+final; slots 8..11 are reserved) */
+   * sweep_team<1024>, 7: above: sweep_hub_scatter+select+final; slots 8..11 are reserved) */
   uint64_t group_edges[12];
   uint64_t group_nodes[12];
   uint64_t group_launches[12];
@@ -121,10 +121,13 @@ const char *kmp_last_error(void);
 /* Fill cfg with the default-preset values for the clusterer (mode 0) or refiner (mode 1). */
 void kmp_lp_default_config(int mode, kmp_lp_config *cfg);
 
-/* Environment knobs read once per handle in kmp_lp_create (experiments / tests only; results never
- * depend on them): KMP_HUB_CAP_PCT = slots of a high-degree vertex's table region per 100 labels
- * (default 300), KMP_HUB_WAVE_SLOTS = 8-byte table slots one wave of high-degree vertices may use
- * (default 2^28 = 2 GiB; smaller values process a sub-round's hubs in more waves). */
+/* Environment knobs (experiments / tests only; results never depend on them). Read once per handle in
+ * kmp_lp_create: KMP_HUB_WAVE_SLOTS = 8-byte bucket entries one wave of high-degree vertices may use (default 2^28 =
+ * 2 GiB; smaller values process a sub-round's hubs in more waves), KMP_HUB_BUCKET_CAP / KMP_HUB_SEL_LIMIT = smaller
+ * bucket capacity / claim limit of the hub tier (force its overflow list and multi-pass selection),
+ * KMP_THREAD_MAX_DEG = 16 sends degrees 17..31 to the warp kernel instead of the register-sort kernel,
+ * KMP_FUSED_COMMIT=0, KMP_OVERLAP_TIERS=0, KMP_FORCE_P64=1, KMP_UPLOAD_OVERLAP=0 (launch structure / word width).
+ * Read per call: KMP_ACTIVATION=push|pull, KMP_TRACE=1 (set_graph stage times on stderr). */
 int kmp_lp_create(const kmp_lp_config *cfg, kmp_lp_handle **out);
 int kmp_lp_destroy(kmp_lp_handle *h);
 

@@ -53,7 +53,7 @@ int fail(int code, const std::string &msg) {
 
 constexpr int kNumGroups = 4; // degree groups of the schedule
 constexpr int kNumTiers = 8;  // kernel tiers: group 1 is split in two, group 3 (deg >= 256) in four
-constexpr int kHubTier = 7;   // deg >= kHubMinDegree: edge-parallel kernels with a global table
+constexpr int kHubTier = 7;   // deg >= kHubMinDegree: edge-parallel kernels, label-partitioned buckets (lp_sweep.cuh)
 constexpr int kStatTiers = 12; // tier slots of kmp_lp_stats / ctr64 (edges at [tier], nodes at [kCtrNodes + tier])
 constexpr int kCtrNodes = 16, kCtrScratch = 40, kCtrSize = 48;
 constexpr uint32_t kHubMinDegree = 8192;       // graphs with edge weights (32-bit ratings in the team tables)
@@ -167,13 +167,13 @@ struct kmp_lp_handle {
   DevBuf<int32_t> incoming, chist, hist, jmin, out_cur, out_delta, ohist, ojmin;
   DevBuf<uint32_t> ctr32; // [0] mover_count [1] moved_count (per iteration) [2] misc
   DevBuf<unsigned long long> ctr64; // [0] edges [1] nodes [2] proposals
-  // tier 4 (deg >= 2048): per list entry the first slot of its global table region, and the
-  // (entry, chunk) work items of phase 1; all per sub-round
+  // hub tier ("t4" in these names is historical): per list entry its first bucket (wave-relative), the
+  // (entry, chunk) work items of the scatter pass and the (entry, bucket) items of the select pass; all per sub-round
   DevBuf<uint32_t> t4_table_off, t4_item_entry, t4_item_chunk, t4_sel_entry, t4_sel_piece, t4_sel_begin;
   DevBuf<uint32_t> t4_item_u, t4_item_beg, t4_item_deg; // static per item: vertex, xadj[u], degree
   std::vector<uint32_t> t4_item_off, t4_sel_off; // S + 1
-  // A sub-round's hubs are processed in waves whose table regions together stay below
-  // hub_wave_slots, so that the table traffic of a wave stays in L2; every wave reuses the same memory.
+  // A sub-round's hubs are processed in waves whose bucket regions together stay below hub_wave_slots entries
+  // (a memory bound: every wave reuses the same regions, cursors and overflow list).
   struct HubWave {
     uint32_t item_lo, item_hi, sel_lo, sel_hi; // absolute ranges in the t4_item_* / t4_sel_* arrays
   };

@@ -8,7 +8,7 @@
 //   tier 5 (deg 1024..4095) sweep_team<T=512> : one 512-thread CTA per vertex, 8192 slots
 //   tier 6 (deg 4096..8191, or ..16383 with unit edge weights: 16-bit ratings) sweep_team<T=1024>: one
 //                          1024-thread CTA per vertex, 16384 / 32768 slots
-//   tier 7 (deg >= 8192 / 16384) sweep_hub_*  : edge-parallel chunks, global 64-bit table (see below)
+//   tier 7 (deg >= 8192 / 16384) sweep_hub_*  : edge-parallel chunks, label-partitioned bucket appends (see below)
 //   (tiers 1-2 are degree group 1 of the schedule, tiers 4..7 group 3)
 //
 // Each of them restates label_propagation.h:460-541 (find_best_cluster): accumulate
