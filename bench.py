@@ -110,11 +110,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.monotonic(), line.strip()))
+
+    def mark_begin(self):
+        """Start of the timed region (the sampler itself is started earlier: nvidia-smi needs > 100 ms to emit its
+        first line, a short timed region would otherwise end with no sample)."""
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = getattr(self, "t_begin", None)
+        t1 = getattr(self, "t_end", None)
+        if t0 is not None and t1 is not None and time.monotonic() - t0 < 0.35:
+            time.sleep(0.35 - (time.monotonic() - t0))  # let at least one more 100 ms tick arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -122,7 +134,16 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        lines = [s for _, s in self.samples]
+        where = "whole sampled interval"
+        if t0 is not None and t1 is not None:
+            inside = [s for t, s in self.samples if t0 <= t <= t1 + 0.05]
+            if inside:
+                lines, where = inside, "timed region"
+            else:  # region shorter than the sampling period: the samples next to it (same kernels before / after)
+                near = [s for t, s in self.samples if t0 - 0.3 <= t <= t1 + 0.3]
+                lines, where = (near or lines), "within 0.3 s of the timed region (region < sampling period)"
+        for s in lines:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 6:
                 continue
@@ -135,7 +156,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": where}
 
 
 def _cpu_worker(name, mode, steps, warmup, host_graph=None):
@@ -200,11 +221,12 @@ def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
     handle.set_timing(False)
     handle.cluster(mcw, fetch=False)
     cl_host = handle.download_labels()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         KC.contract_on_handle(handle, None).close()
-    sampler = ClockSampler(local_rank)
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark_begin()
     tot_ms, launches, last = 0.0, 0, None
     for _ in range(args.steps):
         cg = KC.contract_on_handle(handle, None)
@@ -213,6 +235,7 @@ def contraction_mode(args, handle, g_host, n, m, k, mcw, dev, local_rank):
         last = (cg.stats.c_n, cg.stats.c_m, cg.stats.cut_edges, cg.stats.sort_bits)
         cg.close()
     torch.cuda.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
     value = m * args.steps / (tot_ms * 1e-3)
     c_n, c_m, cut, bits = last
@@ -380,11 +403,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         run_resident()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     tot_ms = 0.0
     edges = nodes = launches = sweeps = 0
     NT = 8  # kernel tiers (include/kaminpar_b200_lp.h kmp_lp_stats)
@@ -406,7 +430,7 @@ def main():
         push_rounds += st.push_rounds
         last = st
     barrier()
-    clocks = sampler.stop()
+    sampler.mark_end()
     # ---- breakdown steps (outside the timed region): per-tier CUDA events, tiers serialised ----------------
     BSTEPS = 2
     (refine_handle or handle).set_timing(True)
@@ -424,6 +448,7 @@ def main():
         push_ms += st.group_sweep_ms[14]
     (refine_handle or handle).set_timing(False)
     barrier()
+    clocks = sampler.stop()
     t = torch.tensor([tot_ms, float(edges)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
