@@ -17,9 +17,8 @@
 // (try_node_move :817-841) -- emit a proposal (u, target) that the commit kernels resolve.
 #pragma once
 
-#include <utility>
-
 #include "lp_device.cuh"
+#include "lp_sortnet.cuh"
 
 namespace kmp {
 
@@ -68,71 +67,6 @@ __device__ __forceinline__ typename LabG<P64>::word load_labg(const SweepArgs &a
 // ~250 per edge (N = 64 was measured too: 230 registers, 1.5-2x slower than the warp kernel on deg 32..64), and consecutive list entries have consecutive adjacency rows, so the per-thread row reads share
 // sectors across the warp.
 // ================================================================================================
-template <bool EW>
-__host__ __device__ __forceinline__ void compare_exchange(uint32_t &ka, uint32_t &kb, int32_t &wa, int32_t &wb) {
-  if (EW) {
-    const bool sw = ka > kb;
-    const uint32_t k0 = sw ? kb : ka, k1 = sw ? ka : kb;
-    const int32_t w0 = sw ? wb : wa, w1 = sw ? wa : wb;
-    ka = k0;
-    kb = k1;
-    wa = w0;
-    wb = w1;
-  } else {
-    const uint32_t lo = ka < kb ? ka : kb, hi = ka < kb ? kb : ka;
-    ka = lo;
-    kb = hi;
-  }
-}
-// The compare-exchange list of Batcher's odd-even merge sort, computed at compile time so that every register
-// index below is a constant (a run-time loop nest would push the arrays into local memory).
-template <int N> struct SortNetwork {
-  static constexpr int kMaxPairs = 576; // N = 64 needs 543
-  int count = 0;
-  unsigned char lo[kMaxPairs] = {}, hi[kMaxPairs] = {};
-};
-template <int N> constexpr SortNetwork<N> make_sort_network() {
-  SortNetwork<N> net{};
-  for (int p = 1; p < N; p <<= 1) {
-    for (int q = p; q >= 1; q >>= 1) {
-      for (int j = q % p; j + q < N; j += 2 * q) {
-        for (int i = 0; i < q; ++i) {
-          if (i + j + q < N && (i + j) / (2 * p) == (i + j + q) / (2 * p)) {
-            net.lo[net.count] = static_cast<unsigned char>(i + j);
-            net.hi[net.count] = static_cast<unsigned char>(i + j + q);
-            ++net.count;
-          }
-        }
-      }
-    }
-  }
-  return net;
-}
-template <int N> struct SortNetworkOf {
-  static constexpr SortNetwork<N> net = make_sort_network<N>();
-};
-template <int N, bool EW, int IDX>
-__host__ __device__ __forceinline__ void sort_step(uint32_t (&k)[N], int32_t (&w)[N]) {
-  if constexpr (IDX < SortNetworkOf<N>::net.count) {
-    constexpr int A = SortNetworkOf<N>::net.lo[IDX];
-    constexpr int B = SortNetworkOf<N>::net.hi[IDX];
-    compare_exchange<EW>(k[A], k[B], w[A], w[B]);
-  }
-}
-template <int N, bool EW, int BASE, int... I>
-__host__ __device__ __forceinline__ void sort_steps(uint32_t (&k)[N], int32_t (&w)[N], std::integer_sequence<int, I...>) {
-  (sort_step<N, EW, BASE + I>(k, w), ...);
-}
-template <int N, bool EW, int... C>
-__host__ __device__ __forceinline__ void sort_chunks(uint32_t (&k)[N], int32_t (&w)[N], std::integer_sequence<int, C...>) {
-  (sort_steps<N, EW, C * 64>(k, w, std::make_integer_sequence<int, 64>{}), ...);
-}
-// ascending by key; the weights travel with their keys (EW only)
-template <int N, bool EW> __host__ __device__ __forceinline__ void sort_registers(uint32_t (&k)[N], int32_t (&w)[N]) {
-  static_assert((N & (N - 1)) == 0 && N <= 64, "network size must be a power of two <= 64");
-  sort_chunks<N, EW>(k, w, std::make_integer_sequence<int, (SortNetworkOf<N>::net.count + 63) / 64>{});
-}
-
 template <int MODE, bool EW, bool P64, int N> __global__ void __launch_bounds__(256) sweep_thread(const SweepArgs a) {
   __shared__ uint32_t s_cnt[2][8]; // proposals per warp of the running CTA iteration (parity-double-buffered)
   __shared__ uint32_t s_base[2];
