@@ -1,4 +1,5 @@
 #!/bin/bash
+# ROUND-1 script (kernel names of that round; round 2: scripts/profile_round2.sh, scripts/final_round2.sh).
 # ncu evidence for profiles/ (run under gpurun on ONE GPU). Numbers printed by bench.py under ncu are
 # not bench values. $1 = tag (file prefix), $2 = "full" to add the --set full capture of the top kernels.
 set -u
