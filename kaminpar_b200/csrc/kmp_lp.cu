@@ -855,7 +855,7 @@ int ensure_lists(kmp_lp_handle *h) {
   KMP_CUDA(h->queue.ensure(static_cast<size_t>(kNumTiers) * kNumGroups * S));
   h->max_list = h->mover_cap;
   h->max_degree = hist[300];
-  // ---- tier 4 metadata: table regions and chunk work items per sub-round ------------------------
+  // ---- hub tier metadata: bucket regions, chunk work items and (entry, bucket) selection items per sub-round --
   {
     const uint32_t t4_begin = h->list_off[kHubTier * S], t4_end = h->list_off[(kHubTier + 1) * S];
     const uint32_t t4_cnt = t4_end - t4_begin;
@@ -1101,8 +1101,9 @@ CommitArgs make_commit_args(kmp_lp_handle *h, const RunCtx &rc) {
   return c;
 }
 
-// A sub-round sg in [0, 4 * S) = (degree group, hashed class). Groups 0..2 have one work list (tier =
-// group); group 3 has the lists of tiers 3..6 (tier 6 = hubs, sharded round-robin instead of by range).
+// A sub-round sg in [0, 4 * S) = (degree group, hashed class). Groups 0 and 2 have one work list (tiers 0 and 3),
+// group 1 has the lists of tiers 1-2, group 3 those of tiers 4..7 (tier 7 = hubs, sharded round-robin instead of by
+// range).
 struct SubRound {
   int group;
   uint32_t sr;
